@@ -1,0 +1,129 @@
+/*
+ * taxi2_b200.h -- C ABI of the B200-native TaxI2 pairwise-distance path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / CUDA types.  Every entry
+ * point replaces one of the two un-vendored native dependencies the reference calls on its hot
+ * path (citations relative to /root/reference/src/itaxotools/taxi2/):
+ *
+ *   Bio.Align.PairwiseAligner(**scores).align(x, y)[0] + _format_pretty   align.py:75,151-157
+ *   calc.seq_distances_{p,p_gaps,jukes_cantor,kimura2p}(x, y)            distances.py:323-347
+ *
+ * All functions return 0 on success or a negative taxi_status; taxi_last_error() gives the text.
+ * No exceptions cross the ABI.  Undefined distances are NaN in fp64 outputs (the Python side maps
+ * them to None exactly as DistanceMetric._is_number does, distances.py:290-292).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * TAXI_E_CUDA.
+ */
+#ifndef TAXI2_B200_H
+#define TAXI2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TAXI_OK = 0,
+    TAXI_E_ARG = -1,      /* bad argument */
+    TAXI_E_EMPTY = -2,    /* zero-length sequence in a pair (Biopython raises ValueError) */
+    TAXI_E_NOMEM = -3,
+    TAXI_E_CUDA = -4,     /* CUDA runtime error / no device */
+    TAXI_E_RANGE = -5     /* scores or lengths outside what the integer DP represents exactly */
+} taxi_status;
+
+typedef struct taxi_ctx taxi_ctx; /* one per (process, device); not thread-safe */
+
+/* Scores.defaults order (align.py:20-27): match, mismatch, internal open, internal extend,
+   end open, end extend.  Integer scores only (Scores is dict[str,int], align.py:17). */
+#define TAXI_NSCORES 6
+
+/* output-selection flags */
+#define TAXI_OUT_SCORE   1u
+#define TAXI_OUT_COUNTS  2u   /* int32[4] per pair: same, transitions, transversions, gap columns */
+#define TAXI_OUT_METRICS 4u   /* double[4] per pair: p, p-gaps, jc, k2p (NaN = undefined)        */
+
+const char* taxi_last_error(void);
+int taxi_abi_version(void);
+int taxi_device_count(void);
+
+int taxi_ctx_create(int device, taxi_ctx** out);
+void taxi_ctx_destroy(taxi_ctx* ctx);
+
+/* Replaces the kwargs of BioPairwiseAligner(**scores), align.py:75. */
+int taxi_set_scores(taxi_ctx* ctx, const int32_t scores[TAXI_NSCORES]);
+
+/*
+ * Encoder/packer: uploads `n` normalized sequences (Sequence.normalize(), sequences.py:20-25)
+ * given as concatenated bytes + offsets[n+1], and keeps them resident in HBM as
+ *   - 1 byte/base class codes for the DP kernels, and
+ *   - 32-column bit planes (2-bit nucleotide + "real" mask + gap mask) for the counting kernel.
+ * set = 0 is the row/query set (x), set = 1 the column/reference set (y); loading set 0 alone
+ * makes it serve as both (versusAll).
+ */
+int taxi_load_sequences(taxi_ctx* ctx, int set, const uint8_t* bytes, const int64_t* offsets, int32_t n);
+
+/*
+ * Align + count + metrics for an explicit pair list (x index into set 0, y index into set 1).
+ * Replaces, per pair:  aligner.align(x, y)[0] -> _format_pretty -> 4 x calc.seq_distances_*.
+ * Host output buffers (any may be NULL if its flag is clear): score int32[n], counts int32[4n],
+ * metrics double[4n].  Host<->device copies happen inside the call.
+ */
+int taxi_align_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,
+                     int32_t* out_score, int32_t* out_counts, double* out_metrics);
+
+/*
+ * Same for the rectangle [x0, x0+nx) x [y0, y0+ny) of SequencePairs.fromProduct (pairs.py:23-25),
+ * row-major: pair p = (x0 + p / ny, y0 + p % ny).  Outputs are host buffers of nx*ny entries.
+ */
+int taxi_align_rect(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                    int32_t* out_score, int32_t* out_counts, double* out_metrics);
+
+/*
+ * Device-resident variant used for kernel-only timing and by callers that keep results in HBM:
+ * the out_* arguments are DEVICE pointers (e.g. torch tensors' data_ptr()), nothing is copied.
+ * The work is enqueued on the context's stream; taxi_sync() waits for it.
+ */
+int taxi_align_rect_device(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                           int32_t* d_score, int32_t* d_counts, double* d_metrics);
+int taxi_sync(taxi_ctx* ctx);
+
+/*
+ * Gapped strings (align.py:151-157 return value).  aln_offsets[npairs+1] are exclusive prefix
+ * sums of the capacities len(x)+len(y) (computed by taxi_alignment_capacity); each alignment is
+ * written right-aligned inside its slot of out_x / out_y and aln_start[p] receives the index of
+ * its first byte, so alignment p is out_x[aln_start[p] : aln_offsets[p+1]].
+ */
+int taxi_alignment_capacity(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs,
+                            int64_t* aln_offsets);
+int taxi_align_strings(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs,
+                       const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
+                       int32_t* out_score);
+
+/*
+ * Alignment-free mode (params.pairs.align = False, versus_all.py:522-530): per-pair counts and
+ * metrics straight from the loaded (pre-aligned) sequences, bit-sliced XOR/popcount.
+ * Replaces calc.seq_distances_* applied to the raw strings (distances.py:323-347).
+ */
+int taxi_count_rect(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                    int32_t* out_counts, double* out_metrics);
+int taxi_count_rect_device(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                           int32_t* d_counts, double* d_metrics);
+int taxi_count_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,
+                     int32_t* out_counts, double* out_metrics);
+
+/*
+ * Best match per query row (versus_reference.py:184-188, decontaminate.py:258-264): first minimum
+ * of metric column `metric` (0..3) over each row of an nx x ny metrics matrix (device pointer,
+ * 4 doubles per pair); NaN never wins.  out_index[x] = -1 when the whole row is undefined.
+ */
+int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
+                            int32_t* out_index_host, double* out_value_host);
+
+/* Telemetry of the last align call: kernels launched, DP cells, device milliseconds. */
+int taxi_last_stats(taxi_ctx* ctx, int64_t* launches, int64_t* cells, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAXI2_B200_H */

@@ -1,0 +1,73 @@
+// Shared declarations of the taxi2_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TAXI_FULL_MASK 0xffffffffu
+
+namespace taxi {
+
+// Values in the DP are score*64 + 6 tag bits.  The tag is the priority of the predecessor
+// state, replicated three times (bits 0-1, 2-3, 4-5) so that one VIMNMX3 both maximises the
+// score and resolves ties in Biopython's order, and the winner's identity survives in the low
+// bits of the result.  See DESIGN.md "tagged maxima".
+constexpr int TAG_BITS = 6;
+constexpr int TAG_MASK = 63;
+constexpr int TAG_REP = 21;  // 0b010101: replicate a 2-bit tag into the three fields
+
+struct ScoreSet {
+    int32_t match, mismatch;      // scaled by 64
+    int32_t io, ie, eo, ee;       // internal/end open/extend, scaled by 64
+    int32_t tagM, tagX, tagY;     // replicated priority tags (1..3)*21
+    int32_t pM, pX, pY;           // plain priorities (1..3)
+};
+
+struct AlignArgs {
+    const uint8_t* xb; const int64_t* xoff;   // row set (x): bytes + offsets
+    const uint8_t* yb; const int64_t* yoff;   // column set (y)
+    const int32_t* px; const int32_t* py;     // explicit pair list, or nullptr for rect mode
+    int32_t x0, y0, ny;                       // rect mode: pair p = (x0 + p / ny, y0 + p % ny)
+    long long npairs;
+    ScoreSet sc;
+    int32_t* score;                           // [npairs] or nullptr
+    int32_t* counts;                          // [npairs][4] or nullptr
+    double* metrics;                          // [npairs][4] or nullptr
+    uint8_t* aln_x; uint8_t* aln_y;           // gapped strings (right-aligned in slots) or nullptr
+    const int64_t* aln_off; int64_t* aln_start;
+    uint8_t* trace; long long trace_per_warp; // traceback arena
+    int32_t* bnd; long long bnd_per_warp;     // stripe-boundary rows (2 ints per column)
+    unsigned long long* counter;              // dynamic work counter
+    int* status;                              // sticky error flag
+};
+
+// 0..3 = A,G,C,T (bit1 = pyrimidine: a transition flips only bit0); 4 = '-'; 5 = missing
+__device__ __forceinline__ int base_class(int c)
+{
+    const int u = c & 0xDF;  // fold ASCII case
+    int k = 5;
+    k = (u == 'A') ? 0 : k;
+    k = (u == 'G') ? 1 : k;
+    k = (u == 'C') ? 2 : k;
+    k = (u == 'T') ? 3 : k;
+    k = (c == '-') ? 4 : k;
+    return k;
+}
+
+// distances.py:319-348 formulas in fp64; NaN where the reference yields None.
+__device__ __forceinline__ void metrics_from_counts(int same, int ts, int tv, int gap, double out[4])
+{
+    const double n = (double)same + (double)ts + (double)tv;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (!(n > 0.0)) { out[0] = out[1] = out[2] = out[3] = nan; return; }
+    const double d = (double)ts + (double)tv;
+    const double p = d / n;
+    out[0] = p;
+    out[1] = (d + (double)gap) / (n + (double)gap);
+    const double P = (double)ts / n, Q = (double)tv / n;
+    const double jc = -0.75 * log(1.0 - 4.0 * p / 3.0);
+    const double k2 = -0.5 * log((1.0 - 2.0 * P - Q) * sqrt(1.0 - 2.0 * Q));
+    out[2] = isfinite(jc) ? jc + 0.0 : nan;
+    out[3] = isfinite(k2) ? k2 + 0.0 : nan;
+}
+
+}  // namespace taxi

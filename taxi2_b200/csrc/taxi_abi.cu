@@ -1,0 +1,613 @@
+// C-ABI of the taxi2_b200 library (see include/taxi2_b200.h): context, sequence residency,
+// kernel dispatch, host<->device staging.  No CPU compute path exists in this file: every
+// entry point that produces results launches a CUDA kernel or fails with TAXI_E_CUDA.
+#include "../../include/taxi2_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "count_planes.cuh"
+#include "gotoh_warp.cuh"
+
+using namespace taxi;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(TAXI_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct SeqSet {
+    bool loaded = false;
+    int32_t n = 0;
+    int32_t maxlen = 0;
+    int64_t total = 0;
+    std::vector<int64_t> off;       // host copy of offsets
+    DevBuf<uint8_t> bytes;          // normalized ASCII (DP kernels compare code points)
+    DevBuf<int64_t> d_off;
+    DevBuf<uint32_t> planes;        // [n][4][W]
+    int32_t W = 0;
+};
+
+}  // namespace
+
+struct taxi_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SeqSet set[2];
+    ScoreSet sc{};
+    int32_t raw_scores[TAXI_NSCORES]{};
+    bool have_scores = false;
+    // scratch
+    DevBuf<uint8_t> trace;
+    DevBuf<int32_t> bnd;
+    DevBuf<unsigned long long> counter;
+    DevBuf<int> status;
+    DevBuf<int32_t> d_px, d_py;
+    DevBuf<int32_t> d_score, d_counts;
+    DevBuf<double> d_metrics;
+    DevBuf<uint8_t> d_alnx, d_alny;
+    DevBuf<int64_t> d_alnoff, d_alnstart;
+    DevBuf<int32_t> d_argidx;
+    DevBuf<double> d_argval;
+    // stats of the last call
+    int64_t launches = 0, cells = 0;
+    double kernel_ms = 0.0;
+};
+
+namespace {
+
+const SeqSet& yset(const taxi_ctx* c) { return c->set[1].loaded ? c->set[1] : c->set[0]; }
+
+int check_ctx(const taxi_ctx* c, bool need_scores)
+{
+    if (!c) return fail(TAXI_E_ARG, "null context");
+    if (!c->set[0].loaded) return fail(TAXI_E_ARG, "no sequences loaded (taxi_load_sequences)");
+    if (need_scores && !c->have_scores) return fail(TAXI_E_ARG, "no scores set (taxi_set_scores)");
+    return TAXI_OK;
+}
+
+// rows-per-lane variants compiled in; 32*H rows form one stripe
+const int kH[] = {4, 8, 12, 16, 21, 24, 32};
+
+int pick_H(int max_rows)
+{
+    // fewest wasted row slots over whole stripes; ties -> larger H (fewer shuffles per cell)
+    int best = 32;
+    long long best_slots = -1;
+    for (int h : kH) {
+        const long long sl = 32LL * h;
+        const long long slots = (max_rows + sl - 1) / sl * sl;
+        if (best_slots < 0 || slots < best_slots || (slots == best_slots && h > best)) { best = h; best_slots = slots; }
+    }
+    return best;
+}
+
+template <int H> cudaError_t occupancy(int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_warp_kernel<H>, GOTOH_WARPS_PER_BLOCK * 32, 0);
+}
+
+template <int H> void launch_gotoh(const AlignArgs& a, int grid, cudaStream_t st)
+{
+    gotoh_warp_kernel<H><<<grid, GOTOH_WARPS_PER_BLOCK * 32, 0, st>>>(a);
+}
+
+struct Dispatch {
+    int H;
+    cudaError_t (*occ)(int*);
+    void (*launch)(const AlignArgs&, int, cudaStream_t);
+    int HB;
+};
+
+const Dispatch kDispatch[] = {
+    {4, occupancy<4>, launch_gotoh<4>, TraceGeom<4>::HB},     {8, occupancy<8>, launch_gotoh<8>, TraceGeom<8>::HB},
+    {12, occupancy<12>, launch_gotoh<12>, TraceGeom<12>::HB}, {16, occupancy<16>, launch_gotoh<16>, TraceGeom<16>::HB},
+    {21, occupancy<21>, launch_gotoh<21>, TraceGeom<21>::HB}, {24, occupancy<24>, launch_gotoh<24>, TraceGeom<24>::HB},
+    {32, occupancy<32>, launch_gotoh<32>, TraceGeom<32>::HB},
+};
+
+// Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
+// pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.
+int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
+{
+    const int H = pick_H(max_rows);
+    const Dispatch* d = nullptr;
+    for (const auto& e : kDispatch) if (e.H == H) d = &e;
+    int bps = 0;
+    CUDA_TRY(d->occ(&bps));
+    if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
+    const long long SL = 32LL * H;
+    const long long nstripes = (max_rows + SL - 1) / SL;
+    const long long per_warp = ((nstripes * (max_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
+    const long long bnd_per_warp = 2LL * (max_cols + 2);
+    // resident warps, capped by pairs and by a trace-arena budget of half the free memory
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    long long warps = (long long)c->sms * bps * GOTOH_WARPS_PER_BLOCK;
+    const long long budget = (long long)((free_b + c->trace.cap) / 2);
+    if (per_warp > budget) return fail(TAXI_E_NOMEM, "one pair needs %lld B of traceback arena, only %lld B available", per_warp, budget);
+    warps = std::min(warps, std::max(1LL, budget / per_warp));
+    warps = std::min(warps, (a.npairs + 0LL));
+    int grid = (int)((warps + GOTOH_WARPS_PER_BLOCK - 1) / GOTOH_WARPS_PER_BLOCK);
+    grid = std::max(grid, 1);
+    const long long gw = (long long)grid * GOTOH_WARPS_PER_BLOCK;
+    CUDA_TRY(c->trace.reserve((size_t)(gw * per_warp)));
+    CUDA_TRY(c->bnd.reserve((size_t)(gw * bnd_per_warp)));
+    CUDA_TRY(c->counter.reserve(1));
+    CUDA_TRY(c->status.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
+    a.sc = c->sc;
+    a.trace = c->trace.p; a.trace_per_warp = per_warp;
+    a.bnd = c->bnd.p; a.bnd_per_warp = bnd_per_warp;
+    a.counter = c->counter.p; a.status = c->status.p;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    d->launch(a, grid, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    return TAXI_OK;
+}
+
+int finish_align(taxi_ctx* c)
+{
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms += ms;
+    int st = 0;
+    CUDA_TRY(cudaMemcpy(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st == TAXI_E_EMPTY) return fail(TAXI_E_EMPTY, "sequence has zero length");
+    if (st != 0) return fail(st, "device status %d", st);
+    return TAXI_OK;
+}
+
+int range_check(const taxi_ctx* c, int max_rows, int max_cols)
+{
+    long long m = 0;
+    for (int k = 0; k < TAXI_NSCORES; ++k) m = std::max<long long>(m, std::llabs((long long)c->raw_scores[k]));
+    // every DP value is bounded by (rows + cols + 2) * max|score|; it must survive the *64 scaling
+    if ((max_rows + (long long)max_cols + 2) * m >= (1LL << 24))
+        return fail(TAXI_E_RANGE, "scores x lengths exceed the exact int32 range of the DP");
+    return TAXI_OK;
+}
+
+void fill_rect(AlignArgs& a, const taxi_ctx* c, int32_t x0, int32_t y0, int32_t ny, long long npairs)
+{
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    a.xb = X.bytes.p; a.xoff = X.d_off.p;
+    a.yb = Y.bytes.p; a.yoff = Y.d_off.p;
+    a.px = a.py = nullptr;
+    a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
+}
+
+int max_len_range(const SeqSet& s, int32_t i0, int32_t n)
+{
+    int m = 0;
+    for (int32_t i = i0; i < i0 + n; ++i) m = std::max<int>(m, (int)(s.off[i + 1] - s.off[i]));
+    return m;
+}
+
+long long cells_rect(const SeqSet& X, const SeqSet& Y, int32_t x0, int32_t nx, int32_t y0, int32_t ny)
+{
+    return (long long)(X.off[x0 + nx] - X.off[x0]) * (long long)(Y.off[y0 + ny] - Y.off[y0]);
+}
+
+int check_rect(const taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny)
+{
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    if (nx < 0 || ny < 0 || x0 < 0 || y0 < 0 || x0 + (long long)nx > X.n || y0 + (long long)ny > Y.n)
+        return fail(TAXI_E_ARG, "rectangle [%d,+%d) x [%d,+%d) outside the loaded sets (%d x %d)", x0, nx, y0, ny, X.n, Y.n);
+    return TAXI_OK;
+}
+
+int upload_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t n, int* max_rows, int* max_cols, long long* cells)
+{
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    int mr = 0, mc = 0;
+    long long cc = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (px[k] < 0 || px[k] >= X.n || py[k] < 0 || py[k] >= Y.n)
+            return fail(TAXI_E_ARG, "pair %lld = (%d, %d) outside the loaded sets", (long long)k, px[k], py[k]);
+        const int la = (int)(X.off[px[k] + 1] - X.off[px[k]]), lb = (int)(Y.off[py[k] + 1] - Y.off[py[k]]);
+        mr = std::max(mr, la); mc = std::max(mc, lb);
+        cc += (long long)la * lb;
+    }
+    CUDA_TRY(c->d_px.reserve((size_t)n));
+    CUDA_TRY(c->d_py.reserve((size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(c->d_px.p, px, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_py.p, py, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    *max_rows = mr; *max_cols = mc;
+    if (cells) *cells = cc;
+    return TAXI_OK;
+}
+
+int reserve_outputs(taxi_ctx* c, int64_t n, uint32_t flags)
+{
+    if (flags & TAXI_OUT_SCORE) CUDA_TRY(c->d_score.reserve((size_t)n));
+    if (flags & TAXI_OUT_COUNTS) CUDA_TRY(c->d_counts.reserve((size_t)n * 4));
+    if (flags & TAXI_OUT_METRICS) CUDA_TRY(c->d_metrics.reserve((size_t)n * 4));
+    return TAXI_OK;
+}
+
+int download_outputs(taxi_ctx* c, int64_t n, uint32_t flags, int32_t* score, int32_t* counts, double* metrics)
+{
+    if ((flags & TAXI_OUT_SCORE) && score)
+        CUDA_TRY(cudaMemcpyAsync(score, c->d_score.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if ((flags & TAXI_OUT_COUNTS) && counts)
+        CUDA_TRY(cudaMemcpyAsync(counts, c->d_counts.p, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if ((flags & TAXI_OUT_METRICS) && metrics)
+        CUDA_TRY(cudaMemcpyAsync(metrics, c->d_metrics.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return TAXI_OK;
+}
+
+void reset_stats(taxi_ctx* c) { c->launches = 0; c->cells = 0; c->kernel_ms = 0.0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* taxi_last_error(void) { return g_error.c_str(); }
+
+int taxi_abi_version(void) { return 1; }
+
+int taxi_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int taxi_ctx_create(int device, taxi_ctx** out)
+{
+    if (!out) return fail(TAXI_E_ARG, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(TAXI_E_CUDA, "CUDA device %d not present (%d visible)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(TAXI_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    taxi_ctx* c = new (std::nothrow) taxi_ctx();
+    if (!c) return fail(TAXI_E_NOMEM, "out of host memory");
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) { delete c; return fail(TAXI_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return TAXI_OK;
+}
+
+void taxi_ctx_destroy(taxi_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& s : c->set) { s.bytes.release(); s.d_off.release(); s.planes.release(); }
+    c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
+    c->d_px.release(); c->d_py.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
+    c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
+    c->d_argidx.release(); c->d_argval.release();
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int taxi_set_scores(taxi_ctx* c, const int32_t s[TAXI_NSCORES])
+{
+    if (!c || !s) return fail(TAXI_E_ARG, "null argument");
+    for (int k = 0; k < TAXI_NSCORES; ++k) {
+        if (std::abs((long long)s[k]) > (1 << 20)) return fail(TAXI_E_RANGE, "score %d out of range", s[k]);
+        c->raw_scores[k] = s[k];
+    }
+    ScoreSet& sc = c->sc;
+    sc.match = s[0] * 64; sc.mismatch = s[1] * 64;
+    sc.io = s[2] * 64; sc.ie = s[3] * 64; sc.eo = s[4] * 64; sc.ee = s[5] * 64;
+    // Biopython picks Needleman-Wunsch when every open == extend, else Gotoh; their path
+    // generators visit co-optimal predecessors in different orders (see oracle/taxi_oracle.c).
+    const bool gotoh = !(s[2] == s[3] && s[4] == s[5]);
+    if (gotoh) { sc.pM = 3; sc.pX = 2; sc.pY = 1; }
+    else       { sc.pM = 1; sc.pX = 2; sc.pY = 3; }
+    sc.tagM = sc.pM * TAG_REP; sc.tagX = sc.pX * TAG_REP; sc.tagY = sc.pY * TAG_REP;
+    c->have_scores = true;
+    return TAXI_OK;
+}
+
+int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_t* offsets, int32_t n)
+{
+    if (!c || (set != 0 && set != 1) || !offsets || n < 0) return fail(TAXI_E_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    SeqSet& s = c->set[set];
+    s.loaded = false;
+    s.off.assign(offsets, offsets + n + 1);
+    if (s.off[0] != 0) return fail(TAXI_E_ARG, "offsets[0] must be 0");
+    s.maxlen = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        if (s.off[i + 1] < s.off[i]) return fail(TAXI_E_ARG, "offsets must be non-decreasing");
+        s.maxlen = std::max<int32_t>(s.maxlen, (int32_t)(s.off[i + 1] - s.off[i]));
+    }
+    s.n = n;
+    s.total = s.off[n];
+    if (s.total > 0 && !bytes) return fail(TAXI_E_ARG, "null bytes");
+    CUDA_TRY(s.bytes.reserve((size_t)s.total + 16));
+    CUDA_TRY(s.d_off.reserve((size_t)n + 1));
+    if (s.total) CUDA_TRY(cudaMemcpyAsync(s.bytes.p, bytes, (size_t)s.total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(s.d_off.p, s.off.data(), ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    s.W = std::max(1, (s.maxlen + 31) / 32);
+    CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * 4 * s.W));
+    if (n > 0) {
+        const long long total = (long long)n * s.W;
+        pack_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s.bytes.p, s.d_off.p, n, s.W, s.planes.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s.loaded = true;
+    if (set == 0 && !c->set[1].loaded) { /* set 0 doubles as the column set */ }
+    return TAXI_OK;
+}
+
+int taxi_sync(taxi_ctx* c)
+{
+    if (!c) return fail(TAXI_E_ARG, "null context");
+    return finish_align(c);
+}
+
+int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                           int32_t* d_score, int32_t* d_counts, double* d_metrics)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const long long npairs = (long long)nx * ny;
+    if (npairs == 0) return TAXI_OK;
+    const int mr = max_len_range(c->set[0], x0, nx), mc = max_len_range(yset(c), y0, ny);
+    if ((rc = range_check(c, mr, mc))) return rc;
+    AlignArgs a{};
+    fill_rect(a, c, x0, y0, ny, npairs);
+    a.score = (flags & TAXI_OUT_SCORE) ? d_score : nullptr;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
+    c->cells += cells_rect(c->set[0], yset(c), x0, nx, y0, ny);
+    return enqueue_align(c, a, mr, mc);
+}
+
+int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                    int32_t* out_score, int32_t* out_counts, double* out_metrics)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    reset_stats(c);
+    const long long npairs = (long long)nx * ny;
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    if (npairs == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if ((rc = reserve_outputs(c, npairs, flags))) return rc;
+    if ((rc = taxi_align_rect_device(c, x0, nx, y0, ny, flags, c->d_score.p, c->d_counts.p, c->d_metrics.p))) return rc;
+    if ((rc = download_outputs(c, npairs, flags, out_score, out_counts, out_metrics))) return rc;
+    return finish_align(c);
+}
+
+int taxi_align_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,
+                     int32_t* out_score, int32_t* out_counts, double* out_metrics)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    reset_stats(c);
+    if (npairs < 0 || (npairs > 0 && (!px || !py))) return fail(TAXI_E_ARG, "bad pair list");
+    if (npairs == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int mr = 0, mc = 0;
+    long long cells = 0;
+    if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, &cells))) return rc;
+    if ((rc = range_check(c, mr, mc))) return rc;
+    if ((rc = reserve_outputs(c, npairs, flags))) return rc;
+    AlignArgs a{};
+    fill_rect(a, c, 0, 0, 1, npairs);
+    a.px = c->d_px.p; a.py = c->d_py.p;
+    a.score = (flags & TAXI_OUT_SCORE) ? c->d_score.p : nullptr;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? c->d_counts.p : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? c->d_metrics.p : nullptr;
+    c->cells += cells;
+    if ((rc = enqueue_align(c, a, mr, mc))) return rc;
+    if ((rc = download_outputs(c, npairs, flags, out_score, out_counts, out_metrics))) return rc;
+    return finish_align(c);
+}
+
+int taxi_alignment_capacity(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs, int64_t* aln_offsets)
+{
+    int rc = check_ctx(c, false);
+    if (rc) return rc;
+    if (npairs < 0 || !aln_offsets || (npairs > 0 && (!px || !py))) return fail(TAXI_E_ARG, "bad argument");
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    aln_offsets[0] = 0;
+    for (int64_t k = 0; k < npairs; ++k) {
+        if (px[k] < 0 || px[k] >= X.n || py[k] < 0 || py[k] >= Y.n)
+            return fail(TAXI_E_ARG, "pair %lld outside the loaded sets", (long long)k);
+        aln_offsets[k + 1] = aln_offsets[k] + (X.off[px[k] + 1] - X.off[px[k]]) + (Y.off[py[k] + 1] - Y.off[py[k]]);
+    }
+    return TAXI_OK;
+}
+
+int taxi_align_strings(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs,
+                       const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
+                       int32_t* out_score)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    reset_stats(c);
+    if (npairs < 0 || (npairs > 0 && (!px || !py || !aln_offsets || !out_x || !out_y || !aln_start)))
+        return fail(TAXI_E_ARG, "bad argument");
+    if (npairs == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int mr = 0, mc = 0;
+    long long cells = 0;
+    if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, &cells))) return rc;
+    if ((rc = range_check(c, mr, mc))) return rc;
+    const int64_t total = aln_offsets[npairs];
+    CUDA_TRY(c->d_alnx.reserve((size_t)total + 16));
+    CUDA_TRY(c->d_alny.reserve((size_t)total + 16));
+    CUDA_TRY(c->d_alnoff.reserve((size_t)npairs + 1));
+    CUDA_TRY(c->d_alnstart.reserve((size_t)npairs));
+    CUDA_TRY(c->d_score.reserve((size_t)npairs));
+    CUDA_TRY(cudaMemcpyAsync(c->d_alnoff.p, aln_offsets, ((size_t)npairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    AlignArgs a{};
+    fill_rect(a, c, 0, 0, 1, npairs);
+    a.px = c->d_px.p; a.py = c->d_py.p;
+    a.score = c->d_score.p;
+    a.aln_x = c->d_alnx.p; a.aln_y = c->d_alny.p; a.aln_off = c->d_alnoff.p; a.aln_start = c->d_alnstart.p;
+    c->cells += cells;
+    if ((rc = enqueue_align(c, a, mr, mc))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_x, c->d_alnx.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_y, c->d_alny.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(aln_start, c->d_alnstart.p, (size_t)npairs * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (out_score) CUDA_TRY(cudaMemcpyAsync(out_score, c->d_score.p, (size_t)npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    return finish_align(c);
+}
+
+static int enqueue_count(taxi_ctx* c, CountArgs a)
+{
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    a.x = Planes{X.planes.p, X.W, X.n};
+    a.y = Planes{Y.planes.p, Y.W, Y.n};
+    CUDA_TRY(c->status.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    const long long blocks = (a.npairs + 255) / 256;
+    count_planes_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    return TAXI_OK;
+}
+
+int taxi_count_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                           int32_t* d_counts, double* d_metrics)
+{
+    int rc = check_ctx(c, false);
+    if (rc) return rc;
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    const long long npairs = (long long)nx * ny;
+    if (npairs == 0) return TAXI_OK;
+    if (npairs > 0x7fffffffLL * 256) return fail(TAXI_E_ARG, "rectangle too large for one launch");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CountArgs a{};
+    a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
+    return enqueue_count(c, a);
+}
+
+int taxi_count_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                    int32_t* out_counts, double* out_metrics)
+{
+    int rc = check_ctx(c, false);
+    if (rc) return rc;
+    reset_stats(c);
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    const long long npairs = (long long)nx * ny;
+    if (npairs == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if ((rc = reserve_outputs(c, npairs, flags & ~TAXI_OUT_SCORE))) return rc;
+    if ((rc = taxi_count_rect_device(c, x0, nx, y0, ny, flags, c->d_counts.p, c->d_metrics.p))) return rc;
+    if ((rc = download_outputs(c, npairs, flags & ~TAXI_OUT_SCORE, nullptr, out_counts, out_metrics))) return rc;
+    return finish_align(c);
+}
+
+int taxi_count_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,
+                     int32_t* out_counts, double* out_metrics)
+{
+    int rc = check_ctx(c, false);
+    if (rc) return rc;
+    reset_stats(c);
+    if (npairs < 0 || (npairs > 0 && (!px || !py))) return fail(TAXI_E_ARG, "bad pair list");
+    if (npairs == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int mr = 0, mc = 0;
+    if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, nullptr))) return rc;
+    if ((rc = reserve_outputs(c, npairs, flags & ~TAXI_OUT_SCORE))) return rc;
+    CountArgs a{};
+    a.px = c->d_px.p; a.py = c->d_py.p; a.npairs = npairs; a.ny = 1;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? c->d_counts.p : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? c->d_metrics.p : nullptr;
+    if ((rc = enqueue_count(c, a))) return rc;
+    if ((rc = download_outputs(c, npairs, flags & ~TAXI_OUT_SCORE, nullptr, out_counts, out_metrics))) return rc;
+    return finish_align(c);
+}
+
+int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
+                            int32_t* out_index_host, double* out_value_host)
+{
+    if (!c || !d_metrics || nx < 0 || ny <= 0 || metric < 0 || metric > 3 || !out_index_host)
+        return fail(TAXI_E_ARG, "bad argument");
+    if (nx == 0) return TAXI_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->d_argidx.reserve((size_t)nx));
+    CUDA_TRY(c->d_argval.reserve((size_t)nx));
+    const int wpb = 8;
+    argmin_rows_kernel<<<(nx + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(d_metrics, nx, ny, metric, c->d_argidx.p, c->d_argval.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out_index_host, c->d_argidx.p, (size_t)nx * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (out_value_host)
+        CUDA_TRY(cudaMemcpyAsync(out_value_host, c->d_argval.p, (size_t)nx * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TAXI_OK;
+}
+
+int taxi_last_stats(taxi_ctx* c, int64_t* launches, int64_t* cells, double* kernel_ms)
+{
+    if (!c) return fail(TAXI_E_ARG, "null context");
+    if (launches) *launches = c->launches;
+    if (cells) *cells = c->cells;
+    if (kernel_ms) *kernel_ms = c->kernel_ms;
+    return TAXI_OK;
+}
+
+}  // extern "C"

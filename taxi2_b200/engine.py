@@ -1,0 +1,216 @@
+"""Batch engine: one context per GPU over the C ABI.  numpy host buffers in, numpy out.
+
+This is the host-side mirror of the two native calls the reference makes per pair
+(/root/reference/src/itaxotools/taxi2/align.py:151-153 and distances.py:323-347), batched.
+PyTorch is optional here and only used by callers that want device-resident outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence as Seq
+
+import numpy as np
+
+from . import _native as N
+
+SCORE_KEYS = (
+    "match_score",
+    "mismatch_score",
+    "internal_open_gap_score",
+    "internal_extend_gap_score",
+    "end_open_gap_score",
+    "end_extend_gap_score",
+)
+DEFAULT_SCORES = (1, -1, -8, -1, -1, -1)
+METRIC_LABELS = ("p", "p-gaps", "jc", "k2p")
+
+
+def scores_vector(scores) -> np.ndarray:
+    if scores is None:
+        scores = DEFAULT_SCORES
+    if isinstance(scores, dict):
+        scores = [scores[k] for k in SCORE_KEYS]
+    vals = []
+    for s in scores:
+        if float(s) != int(s):
+            raise ValueError(f"taxi2_b200 aligns with integer scores only (got {s!r}); Scores is dict[str, int]")
+        vals.append(int(s))
+    if len(vals) != 6:
+        raise ValueError("expected six scores")
+    return np.asarray(vals, dtype=np.int32)
+
+
+def pack_strings(seqs: Iterable[str | bytes]) -> tuple[np.ndarray, np.ndarray]:
+    """list of str/bytes -> (uint8 concatenation, int64 offsets[n+1])"""
+    bs = [s.encode("latin-1", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum([len(b) for b in bs], out=off[1:])
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8) if bs else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+def _p(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One GPU context.  Not thread-safe; create one per device (one process per GPU)."""
+
+    def __init__(self, device: int = 0, scores=None):
+        self._lib = N.load()
+        self._ctx = C.c_void_p()
+        N.check(self._lib.taxi_ctx_create(int(device), C.byref(self._ctx)))
+        self.device = int(device)
+        self.n = [0, 0]
+        self.set_scores(scores)
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.taxi_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration -----------------------------------------------------------------------
+    def set_scores(self, scores) -> None:
+        v = scores_vector(scores)
+        N.check(self._lib.taxi_set_scores(self._ctx, v.ctypes.data_as(C.POINTER(C.c_int32))))
+        self.scores = tuple(int(s) for s in v)
+
+    def load(self, seqs, which: int = 0) -> None:
+        """Upload a sequence set (list of str/bytes, or (bytes, offsets) arrays). 0 = x/rows, 1 = y/columns."""
+        if isinstance(seqs, tuple) and len(seqs) == 2 and isinstance(seqs[0], np.ndarray):
+            data, off = seqs
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            off = np.ascontiguousarray(off, dtype=np.int64)
+        else:
+            data, off = pack_strings(seqs)
+        N.check(self._lib.taxi_load_sequences(self._ctx, int(which), _p(data), _p(off), len(off) - 1))
+        self.n[which] = len(off) - 1
+        if which == 0 and self.n[1] == 0:
+            self._y_is_x = True
+        if which == 1:
+            self._y_is_x = False
+
+    @property
+    def ny(self) -> int:
+        return self.n[0] if getattr(self, "_y_is_x", True) else self.n[1]
+
+    # -- aligned path ------------------------------------------------------------------------
+    def align_rect(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics")) -> dict:
+        npairs = nx * ny
+        flags, score, counts, metrics = self._outputs(npairs, want)
+        N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, _p(score), _p(counts), _p(metrics)))
+        return self._result(score, counts, metrics, (nx, ny))
+
+    def align_pairs(self, px, py, want=("score", "counts", "metrics")) -> dict:
+        px = np.ascontiguousarray(px, dtype=np.int32)
+        py = np.ascontiguousarray(py, dtype=np.int32)
+        flags, score, counts, metrics = self._outputs(len(px), want)
+        N.check(self._lib.taxi_align_pairs(self._ctx, _p(px), _p(py), len(px), flags, _p(score), _p(counts), _p(metrics)))
+        return self._result(score, counts, metrics, None)
+
+    def align_strings(self, px, py) -> tuple[list[bytes], list[bytes], np.ndarray]:
+        """-> (aligned x, aligned y, scores) for each pair, Biopython's first alignment."""
+        px = np.ascontiguousarray(px, dtype=np.int32)
+        py = np.ascontiguousarray(py, dtype=np.int32)
+        n = len(px)
+        off = np.zeros(n + 1, dtype=np.int64)
+        N.check(self._lib.taxi_alignment_capacity(self._ctx, _p(px), _p(py), n, _p(off)))
+        total = int(off[-1])
+        ox = np.zeros(max(total, 1), dtype=np.uint8)
+        oy = np.zeros(max(total, 1), dtype=np.uint8)
+        start = np.zeros(max(n, 1), dtype=np.int64)
+        score = np.zeros(max(n, 1), dtype=np.int32)
+        N.check(self._lib.taxi_align_strings(self._ctx, _p(px), _p(py), n, _p(off), _p(ox), _p(oy), _p(start), _p(score)))
+        bx, by = ox.tobytes(), oy.tobytes()
+        ax = [bx[int(start[k]): int(off[k + 1])] for k in range(n)]
+        ay = [by[int(start[k]): int(off[k + 1])] for k in range(n)]
+        return ax, ay, score[:n]
+
+    def align_rect_device(self, x0, nx, y0, ny, d_score=0, d_counts=0, d_metrics=0) -> None:
+        """Enqueue on the context stream with DEVICE output pointers (ints, e.g. tensor.data_ptr())."""
+        flags = (N.OUT_SCORE if d_score else 0) | (N.OUT_COUNTS if d_counts else 0) | (N.OUT_METRICS if d_metrics else 0)
+        N.check(self._lib.taxi_align_rect_device(self._ctx, x0, nx, y0, ny, flags,
+                                                 C.c_void_p(d_score), C.c_void_p(d_counts), C.c_void_p(d_metrics)))
+
+    # -- alignment-free path -----------------------------------------------------------------
+    def count_rect(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics")) -> dict:
+        flags, _, counts, metrics = self._outputs(nx * ny, want)
+        N.check(self._lib.taxi_count_rect(self._ctx, x0, nx, y0, ny, flags, _p(counts), _p(metrics)))
+        return self._result(None, counts, metrics, (nx, ny))
+
+    def count_pairs(self, px, py, want=("counts", "metrics")) -> dict:
+        px = np.ascontiguousarray(px, dtype=np.int32)
+        py = np.ascontiguousarray(py, dtype=np.int32)
+        flags, _, counts, metrics = self._outputs(len(px), want)
+        N.check(self._lib.taxi_count_pairs(self._ctx, _p(px), _p(py), len(px), flags, _p(counts), _p(metrics)))
+        return self._result(None, counts, metrics, None)
+
+    def count_rect_device(self, x0, nx, y0, ny, d_counts=0, d_metrics=0) -> None:
+        flags = (N.OUT_COUNTS if d_counts else 0) | (N.OUT_METRICS if d_metrics else 0)
+        N.check(self._lib.taxi_count_rect_device(self._ctx, x0, nx, y0, ny, flags, C.c_void_p(d_counts), C.c_void_p(d_metrics)))
+
+    def argmin_rows_device(self, d_metrics: int, nx: int, ny: int, metric: int) -> tuple[np.ndarray, np.ndarray]:
+        idx = np.zeros(nx, dtype=np.int32)
+        val = np.zeros(nx, dtype=np.float64)
+        N.check(self._lib.taxi_argmin_rows_device(self._ctx, C.c_void_p(d_metrics), nx, ny, metric, _p(idx), _p(val)))
+        return idx, val
+
+    def sync(self) -> None:
+        N.check(self._lib.taxi_sync(self._ctx))
+
+    def stats(self) -> dict:
+        launches, cells, ms = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+        N.check(self._lib.taxi_last_stats(self._ctx, C.byref(launches), C.byref(cells), C.byref(ms)))
+        return dict(launches=launches.value, cells=cells.value, kernel_ms=ms.value)
+
+    # -- helpers -----------------------------------------------------------------------------
+    @staticmethod
+    def _outputs(n: int, want: Seq[str]):
+        flags = 0
+        score = counts = metrics = None
+        if "score" in want:
+            flags |= N.OUT_SCORE
+            score = np.zeros(max(n, 1), dtype=np.int32)[:n]
+        if "counts" in want:
+            flags |= N.OUT_COUNTS
+            counts = np.zeros((max(n, 1), 4), dtype=np.int32)[:n]
+        if "metrics" in want:
+            flags |= N.OUT_METRICS
+            metrics = np.full((max(n, 1), 4), np.nan, dtype=np.float64)[:n]
+        return flags, score, counts, metrics
+
+    @staticmethod
+    def _result(score, counts, metrics, shape):
+        out = {}
+        if score is not None:
+            out["score"] = score.reshape(shape) if shape else score
+        if counts is not None:
+            out["counts"] = counts.reshape(*shape, 4) if shape else counts
+        if metrics is not None:
+            out["metrics"] = metrics.reshape(*shape, 4) if shape else metrics
+        return out
+
+
+_engines: dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (lazily created; raises without a GPU)."""
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = Engine(device)
+    return eng

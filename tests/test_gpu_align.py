@@ -1,0 +1,185 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle, bit-exact for scores,
+counts and alignment strings; 1e-12 relative for the fp64 metrics (north star tolerance)."""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from synth import coi_like, random_pairs, read_tab_sequences
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12  # JC / K2P: fp64 log/sqrt on device vs glibc
+
+ALIGN = json.loads((GOLDEN / "align_cases.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from taxi2_b200.engine import Engine
+
+    eng = Engine(0)
+    yield eng
+    eng.close()
+
+
+def assert_metrics_close(got: np.ndarray, want: np.ndarray):
+    assert got.shape == want.shape
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w)
+    g, w = got[~nan_g], want[~nan_w]
+    assert np.all(np.abs(g - w) <= REL_TOL * np.maximum(np.abs(w), 1e-300) + 0.0) or np.allclose(g, w, rtol=REL_TOL, atol=0.0)
+    # p and p-gaps are a single IEEE division of exact integers: bit-exact
+    assert np.array_equal(got[:, :2][~nan_g[:, :2]], want[:, :2][~nan_w[:, :2]])
+
+
+def oracle_batch(xs, ys, px, py, scores):
+    from taxi2_b200.engine import pack_strings
+
+    data, off = pack_strings(list(xs) + list(ys))
+    return oracle.align_count_pairs(data, off, np.asarray(px), np.asarray(py) + len(xs), scores)
+
+
+def check_pairs(engine, xs, ys, scores, strings=True):
+    engine.set_scores(scores)
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    n = len(xs)
+    px = np.arange(n, dtype=np.int32)
+    got = engine.align_pairs(px, px)
+    want = oracle_batch(xs, ys, px, px, scores)
+    assert np.array_equal(got["score"], want["score"])
+    assert np.array_equal(got["counts"], want["counts"])
+    assert_metrics_close(got["metrics"], want["metrics"])
+    if strings:
+        ax, ay, sc = engine.align_strings(px, px)
+        assert np.array_equal(sc, want["score"])
+        for k in range(n):
+            ox, oy, _ = oracle.align(xs[k], ys[k], scores)
+            assert ax[k].decode("latin-1") == ox and ay[k].decode("latin-1") == oy, (k, xs[k], ys[k])
+
+
+@pytest.mark.parametrize("case", ALIGN["align_tests"] + ALIGN["align_tests_failing"],
+                         ids=lambda c: f"{c['x']}-{c['y']}-{c['scores']}")
+def test_reference_known_answers(engine, case):
+    """tests/test_align.py of the reference, through the CUDA path."""
+    engine.set_scores(case["scores"])
+    engine.load([case["x"]], 0)
+    engine.load([case["y"]], 1)
+    ax, ay, sc = engine.align_strings([0], [0])
+    got = [ax[0].decode(), ay[0].decode()]
+    assert got in case["solutions"]
+    ox, oy, oscore = oracle.align(case["x"], case["y"], case["scores"])
+    assert got == [ox, oy] and sc[0] == oscore
+    if "biopython" in case:
+        assert got == case["biopython"]["aligned"] and sc[0] == case["biopython"]["score"]
+
+
+@pytest.mark.parametrize("scores", [(1, -1, -8, -1, -1, -1), (1, 0, 0, 0, 0, 0), (2, -3, -5, -2, -4, -1),
+                                    (1, -1, -1, -1, -2, -2), (10, 0, -10, -6, 0, 0), (1, -1, -8, -1, -3, -2),
+                                    (1, 0, 0, -2, -1, 0), (0, 1, -1, 0, 0, 0)])
+def test_random_short_pairs(engine, scores):
+    rng = np.random.default_rng(hash(scores) % (2**32))
+    xs, ys = random_pairs(rng, 300, 1, 70, sub=0.25, indel=0.08)
+    check_pairs(engine, xs, ys, scores)
+
+
+def test_low_complexity_ties(engine):
+    """Two-letter alphabets maximise co-optimal paths: stresses the tie-breaking order."""
+    rng = np.random.default_rng(7)
+    xs, ys = random_pairs(rng, 400, 1, 90, sub=0.3, indel=0.1, alphabet=b"AT")
+    for scores in [(1, -1, -8, -1, -1, -1), (1, -1, -2, -1, -1, -1), (1, 0, 0, 0, 0, 0), (1, -1, -1, -1, -1, -1)]:
+        check_pairs(engine, xs, ys, scores)
+
+
+def test_barcode_length_pairs(engine):
+    rng = np.random.default_rng(650)
+    xs, ys = random_pairs(rng, 64, 560, 700, sub=0.12, indel=0.02)
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1))
+
+
+def test_multi_stripe_long_pairs(engine):
+    """Lengths above one 32*H stripe: rows cross the stripe-boundary buffer."""
+    rng = np.random.default_rng(1500)
+    xs, ys = random_pairs(rng, 12, 1100, 1700, sub=0.1, indel=0.02)
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1))
+    xs, ys = random_pairs(rng, 3, 2500, 3300, sub=0.1, indel=0.02)
+    check_pairs(engine, xs, ys, (2, -1, -3, -2, -1, -1))
+
+
+def test_ragged_and_tiny(engine):
+    xs = [b"A", b"A", b"ACGT" * 40, b"T", b"ACGTN", b"NNNN", b"A" * 33, b"C" * 129]
+    ys = [b"A", b"C", b"G", b"ACGT" * 50, b"NNNNN", b"ACGT", b"A" * 31, b"C" * 64 + b"G" + b"C" * 64]
+    for scores in [(1, -1, -8, -1, -1, -1), (1, 0, 0, 0, 0, 0)]:
+        check_pairs(engine, xs, ys, scores)
+
+
+def test_empty_sequence_raises(engine):
+    engine.set_scores(None)
+    engine.load([b"ACGT", b""], 0)
+    engine.load([b"ACGT"], 1)
+    with pytest.raises(ValueError):
+        engine.align_pairs([1], [0])
+
+
+def test_sample_120_all_pairs(engine):
+    """BASELINE config 1: versusAll on Taxi2test1_120.tab, full ordered N x N product."""
+    _, seqs = read_tab_sequences(GOLDEN / "Taxi2test1_120.tab")
+    n = len(seqs)
+    engine.set_scores(None)
+    engine.load(seqs, 0)
+    engine._y_is_x = True
+    got = engine.align_rect(0, n, 0, n)
+    from taxi2_b200.engine import pack_strings
+
+    data, off = pack_strings(seqs)
+    px, py = np.divmod(np.arange(n * n, dtype=np.int64), n)
+    want = oracle.align_count_pairs(data, off, px.astype(np.int32), py.astype(np.int32))
+    assert np.array_equal(got["score"].ravel(), want["score"])
+    assert np.array_equal(got["counts"].reshape(-1, 4), want["counts"])
+    assert_metrics_close(got["metrics"].reshape(-1, 4), want["metrics"])
+
+
+def test_coi_rect_vs_oracle(engine):
+    seqs = coi_like(96, seed=3)
+    engine.set_scores(None)
+    engine.load(seqs[:32], 0)
+    engine.load(seqs[32:], 1)
+    got = engine.align_rect(0, 32, 0, 64)
+    px, py = np.divmod(np.arange(32 * 64), 64)
+    want = oracle_batch(seqs[:32], seqs[32:], px, py, None)
+    assert np.array_equal(got["score"].ravel(), want["score"])
+    assert np.array_equal(got["counts"].reshape(-1, 4), want["counts"])
+    assert_metrics_close(got["metrics"].reshape(-1, 4), want["metrics"])
+
+
+def test_prealigned_counts(engine):
+    """Alignment-free bit-sliced path vs the oracle's string scan, incl. the reference's metrics.tsv."""
+    rows = json.loads((GOLDEN / "metrics_cases.json").read_text())["rows"]
+    xs = [r["x"] for r in rows] + ["gg-ccnccta", "---"]
+    ys = [r["y"] for r in rows] + ["ggaccaccaa", "nnn"]
+    rng = np.random.default_rng(11)
+    al = np.frombuffer(b"ACGTacgt-N?RY", dtype=np.uint8)
+    for _ in range(300):
+        L1, L2 = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        xs.append(al[rng.integers(0, len(al), L1)].tobytes().decode())
+        ys.append(al[rng.integers(0, len(al), L2)].tobytes().decode())
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    px = np.arange(len(xs), dtype=np.int32)
+    got = engine.count_pairs(px, px)
+    for k in range(len(xs)):
+        c = oracle.count(xs[k], ys[k])
+        want_c = c if c else (0, 0, 0, 0)
+        assert tuple(got["counts"][k]) == tuple(want_c), (k, xs[k], ys[k])
+        want_m = np.array(oracle.metrics(want_c))
+        assert_metrics_close(got["metrics"][k:k + 1], want_m[None, :])
+    rect = engine.count_rect(0, 40, 0, 50)
+    for i in range(40):
+        for j in range(50):
+            c = oracle.count(xs[i], ys[j]) or (0, 0, 0, 0)
+            assert tuple(rect["counts"][i, j]) == tuple(c)

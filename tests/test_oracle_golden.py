@@ -1,0 +1,70 @@
+"""Pins the CPU oracle against every known-answer vector the reference's tests hold for the
+path: tests/test_align.py (53 cases) and tests/test_distances (26x4 + 3)."""
+from __future__ import annotations
+
+import json
+import math
+
+import pytest
+
+import oracle
+
+from conftest import GOLDEN
+
+ALIGN = json.loads((GOLDEN / "align_cases.json").read_text())
+METRICS = json.loads((GOLDEN / "metrics_cases.json").read_text())
+
+
+@pytest.mark.parametrize("case", ALIGN["align_tests"], ids=lambda c: f"{c['x']}-{c['y']}-{c['scores']}")
+def test_align_known_answers(case):
+    ax, ay, _ = oracle.align(case["x"], case["y"], case["scores"])
+    assert len(ax) == len(ay)
+    assert [ax, ay] in case["solutions"]
+
+
+@pytest.mark.parametrize("case", ALIGN["align_tests_failing"], ids=lambda c: f"{c['x']}-{c['y']}")
+def test_align_biopython_only_cases(case):
+    # the reference records Biopython's own alignment and score for these (test_align.py:170-202)
+    ax, ay, score = oracle.align(case["x"], case["y"], case["scores"])
+    assert [ax, ay] == case["biopython"]["aligned"]
+    assert score == case["biopython"]["score"]
+    assert [ax, ay] in case["solutions"]
+
+
+def test_algorithm_selection():
+    assert oracle.uses_gotoh((1, -1, -8, -1, -1, -1))
+    assert not oracle.uses_gotoh((1, 0, 0, 0, 0, 0))
+    assert not oracle.uses_gotoh((1, -1, -1, -1, -2, -2))
+    assert oracle.uses_gotoh((1, 0, 0, 0, -2, 0))
+
+
+def test_empty_sequence_raises():
+    with pytest.raises(ValueError):
+        oracle.align("", "ACGT")
+
+
+@pytest.mark.parametrize("row", METRICS["rows"], ids=lambda r: f"{r['x']}-{r['y']}")
+def test_metrics_file(row):
+    c = oracle.count(row["x"], row["y"])
+    got = oracle.metrics(c) if c else (math.nan,) * 4
+    for g, e in zip(got, row["expected"]):
+        if e is None:
+            assert math.isnan(g)
+        else:
+            assert abs(g - e) <= METRICS["tolerance"]
+
+
+def test_metrics_exact():
+    idx = {label: k for k, label in enumerate(METRICS["labels"])}
+    for case in METRICS["exact"]:
+        c = oracle.count(case["x"], case["y"])
+        got = oracle.metrics(c)[idx[case["metric"]]] if c else math.nan
+        if case["expected"] is None:
+            assert math.isnan(got)
+        else:
+            assert got == case["expected"]
+
+
+def test_zero_distance_is_positive_zero():
+    m = oracle.metrics(oracle.count("ACGT", "ACGT"))
+    assert all(v == 0.0 and math.copysign(1.0, v) == 1.0 for v in m)
