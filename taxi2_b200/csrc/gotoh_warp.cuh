@@ -182,55 +182,78 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
     fin = __shfl_sync(TAXI_FULL_MASK, fin, l_last);
     __syncwarp();
 
-    if (lane != 0) return;
-
-    // ---- first-path traceback + fused distance counts (lane 0) -------------------------------
+    // ---- first-path traceback + fused distance counts, warp-parallel --------------------------
+    // The walk is sequential by nature, but it moves in long straight runs (diagonal runs between
+    // indels).  Each iteration the 32 lanes fetch the trace codes of the next 32 cells straight
+    // ahead in the current direction, a ballot finds how far the path really goes that way, and
+    // the columns of that run are classified and counted with ballots.  ~70 iterations per
+    // 650 bp pair instead of ~1300 dependent loads.
     int state = state_of_tag(fin & 3, sc);
     int i = nA, j = nB;
     int same = 0, ts = 0, tv = 0, gapc = 0, pend = 0;
     bool seen = false;
     const bool strings = a.aln_x != nullptr;
     int64_t wpos = strings ? a.aln_off[p + 1] : 0;
-    uint8_t* ox = a.aln_x;
-    uint8_t* oy = a.aln_y;
     while (i > 0 && j > 0) {
-        const int q = (i - 1) % SL;
-        const int l = q / H, r = q % H, s = (i - 1) / SL;
-        const int tb = (int)__ldcg(trace + ((size_t)(s * step_stride + (j - 1 + l)) * 32 + l) * HB + r);
-        const int ca = (int)__ldg(x + i - 1), cb = (int)__ldg(y + j - 1);
-        const int ka = base_class(ca), kb = base_class(cb);
-        int tag;
-        if (state == 0) {
-            tag = tb & 3;
-            if (ka < 4 && kb < 4) {
-                if (seen) gapc += pend;
-                pend = 0; seen = true;
-                const int d = ka ^ kb;
-                same += (d == 0); ts += (d == 1); tv += (d > 1);
-            } else if ((ka == 4 && kb < 4) || (kb == 4 && ka < 4)) {
-                ++pend;
-            }
-            if (strings) { --wpos; ox[wpos] = (uint8_t)ca; oy[wpos] = (uint8_t)cb; }
-            --i; --j;
-        } else if (state == 1) {
-            tag = (tb >> 2) & 3;
-            pend += (ka < 4);
-            if (strings) { --wpos; ox[wpos] = (uint8_t)ca; oy[wpos] = '-'; }
-            --i;
-        } else {
-            tag = (tb >> 4) & 3;
-            pend += (kb < 4);
-            if (strings) { --wpos; ox[wpos] = '-'; oy[wpos] = (uint8_t)cb; }
-            --j;
+        const int di = (state != 2), dj = (state != 1);
+        const int ii = i - lane * di, jj = j - lane * dj;
+        const bool valid = ii >= 1 && jj >= 1;
+        int tb = 0, ca = 0, cb = 0;
+        if (valid) {
+            const int q = (ii - 1) % SL;
+            const int l = q / H, r = q % H, s = (ii - 1) / SL;
+            tb = (int)__ldcg(trace + ((size_t)(s * step_stride + (jj - 1 + l)) * 32 + l) * HB + r);
+            ca = (int)__ldg(x + ii - 1);
+            cb = (int)__ldg(y + jj - 1);
         }
-        state = state_of_tag(tag, sc);
+        const int tag = (tb >> (2 * state)) & 3;
+        const int own = state == 0 ? sc.pM : (state == 1 ? sc.pX : sc.pY);
+        const unsigned cont = __ballot_sync(TAXI_FULL_MASK, valid && tag == own);
+        const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, valid);
+        // lanes 0..f are visited in this state, f = first lane whose pointer leaves the run
+        const int f = __ffs(~cont) - 1;                     // 0..31, or -1 when all 32 continue
+        int V = (f < 0) ? 32 : f + 1;
+        V = min(V, __popc(vmask));
+        const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
+        const int last_tag = __shfl_sync(TAXI_FULL_MASK, tag, V - 1);
+        // classify my column
+        const int ka = (state == 2) ? 4 : base_class(ca);
+        const int kb = (state == 1) ? 4 : base_class(cb);
+        const bool both = ka < 4 && kb < 4;
+        const int d = ka ^ kb;
+        const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
+        const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
+        const unsigned tsm = __ballot_sync(TAXI_FULL_MASK, both && d == 1) & visited;
+        const unsigned tvm = __ballot_sync(TAXI_FULL_MASK, both && d > 1) & visited;
+        if (bm) {
+            ts += __popc(tsm); tv += __popc(tvm); same += __popc(bm & ~(tsm | tvm));
+            const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
+            const unsigned below = (1u << fb) - 1u;                           // visited before the first both-real column
+            const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
+            if (seen) gapc += pend + __popc(gm & below);
+            gapc += __popc(gm & upto & ~below);
+            pend = __popc(gm & ~upto);
+            seen = true;
+        } else {
+            pend += __popc(gm);
+        }
+        if (strings && lane < V) {
+            a.aln_x[wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
+            a.aln_y[wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
+        }
+        wpos -= V;
+        i -= V * di; j -= V * dj;
+        state = state_of_tag(last_tag, sc);
     }
     if (strings) {
         // leading end gap: whatever is left of x (vertical) or y (horizontal)
-        while (i > 0) { --wpos; ox[wpos] = __ldg(x + i - 1); oy[wpos] = '-'; --i; }
-        while (j > 0) { --wpos; ox[wpos] = '-'; oy[wpos] = __ldg(y + j - 1); --j; }
-        a.aln_start[p] = wpos;
+        for (int k = lane; k < i; k += 32) { a.aln_x[wpos - 1 - k] = __ldg(x + i - 1 - k); a.aln_y[wpos - 1 - k] = '-'; }
+        wpos -= i;
+        for (int k = lane; k < j; k += 32) { a.aln_x[wpos - 1 - k] = '-'; a.aln_y[wpos - 1 - k] = __ldg(y + j - 1 - k); }
+        wpos -= j;
+        if (lane == 0) a.aln_start[p] = wpos;
     }
+    if (lane != 0) return;
     if (a.score) a.score[p] = fin >> TAG_BITS;
     if (a.counts) {
         *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);

@@ -194,7 +194,7 @@ int finish_align(taxi_ctx* c)
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms += ms;
     int st = 0;
-    CUDA_TRY(cudaMemcpy(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (c->status.p) CUDA_TRY(cudaMemcpy(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost));
     if (st == TAXI_E_EMPTY) return fail(TAXI_E_EMPTY, "sequence has zero length");
     if (st != 0) return fail(st, "device status %d", st);
     return TAXI_OK;
@@ -220,6 +220,12 @@ void fill_rect(AlignArgs& a, const taxi_ctx* c, int32_t x0, int32_t y0, int32_t 
     a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
 }
 
+bool has_empty(const SeqSet& s, int32_t i0, int32_t n)
+{
+    for (int32_t i = i0; i < i0 + n; ++i) if (s.off[i + 1] == s.off[i]) return true;
+    return false;
+}
+
 int max_len_range(const SeqSet& s, int32_t i0, int32_t n)
 {
     int m = 0;
@@ -241,7 +247,8 @@ int check_rect(const taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny
     return TAXI_OK;
 }
 
-int upload_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t n, int* max_rows, int* max_cols, long long* cells)
+int upload_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t n, int* max_rows, int* max_cols, long long* cells,
+                 bool need_nonempty = true)
 {
     const SeqSet& X = c->set[0];
     const SeqSet& Y = yset(c);
@@ -251,6 +258,8 @@ int upload_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t n, i
         if (px[k] < 0 || px[k] >= X.n || py[k] < 0 || py[k] >= Y.n)
             return fail(TAXI_E_ARG, "pair %lld = (%d, %d) outside the loaded sets", (long long)k, px[k], py[k]);
         const int la = (int)(X.off[px[k] + 1] - X.off[px[k]]), lb = (int)(Y.off[py[k] + 1] - Y.off[py[k]]);
+        if (need_nonempty && (la == 0 || lb == 0))
+            return fail(TAXI_E_EMPTY, "sequence has zero length (pair %lld)", (long long)k);
         mr = std::max(mr, la); mc = std::max(mc, lb);
         cc += (long long)la * lb;
     }
@@ -405,6 +414,8 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     CUDA_TRY(cudaSetDevice(c->device));
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
+    if (has_empty(c->set[0], x0, nx) || has_empty(yset(c), y0, ny))
+        return fail(TAXI_E_EMPTY, "sequence has zero length");
     const int mr = max_len_range(c->set[0], x0, nx), mc = max_len_range(yset(c), y0, ny);
     if ((rc = range_check(c, mr, mc))) return rc;
     AlignArgs a{};
@@ -570,7 +581,7 @@ int taxi_count_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t 
     if (npairs == 0) return TAXI_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     int mr = 0, mc = 0;
-    if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, nullptr))) return rc;
+    if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, nullptr, false))) return rc;
     if ((rc = reserve_outputs(c, npairs, flags & ~TAXI_OUT_SCORE))) return rc;
     CountArgs a{};
     a.px = c->d_px.p; a.py = c->d_py.p; a.npairs = npairs; a.ny = 1;
