@@ -71,6 +71,8 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def __enter__(self):
+        if self.gpu < 0:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
@@ -235,12 +237,20 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    debug = bool(os.environ.get("TAXI_BENCH_DEBUG"))
+
     def step_device(k: int) -> int:
         x0, y0 = tile_of(k, rank, world, n)
+        ta = time.perf_counter()
         flush.zero_()
         torch.cuda.synchronize()
+        tb = time.perf_counter()
         eng.align_rect_device(x0, TILE_X, y0, TILE_Y, 0, d_counts.data_ptr(), d_metrics.data_ptr())
+        tc = time.perf_counter()
         eng.sync()
+        td = time.perf_counter()
+        if debug:
+            print(f"step {k}: flush {1e3*(tb-ta):.1f} ms, enqueue {1e3*(tc-tb):.1f} ms, sync {1e3*(td-tc):.1f} ms", file=sys.stderr)
         return int(lens[x0:x0 + TILE_X].sum()) * int(lens[y0:y0 + TILE_Y].sum())
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
@@ -248,7 +258,7 @@ def main() -> None:
         step_device(k)
     st0 = eng.stats()
     barrier()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank if not os.environ.get('TAXI_NO_SAMPLER') else -1) as clocks:
         t0 = time.perf_counter()
         cells = 0
         for k in range(args.steps):

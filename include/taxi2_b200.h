@@ -58,8 +58,9 @@ int taxi_set_scores(taxi_ctx* ctx, const int32_t scores[TAXI_NSCORES]);
  * given as concatenated bytes + offsets[n+1], and keeps them resident in HBM as
  *   - 1 byte/base class codes for the DP kernels, and
  *   - 32-column bit planes (2-bit nucleotide + "real" mask + gap mask) for the counting kernel.
- * set = 0 is the row/query set (x), set = 1 the column/reference set (y); loading set 0 alone
- * makes it serve as both (versusAll).
+ * set = 0 is the row/query set (x), set = 1 the column/reference set (y).  Loading set 0 discards
+ * any previous set 1 and makes set 0 serve as both (versusAll); load set 1 afterwards for
+ * query x reference work (versusReference).
  */
 int taxi_load_sequences(taxi_ctx* ctx, int set, const uint8_t* bytes, const int64_t* offsets, int32_t n);
 

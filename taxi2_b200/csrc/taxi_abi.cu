@@ -395,7 +395,7 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     s.loaded = true;
-    if (set == 0 && !c->set[1].loaded) { /* set 0 doubles as the column set */ }
+    if (set == 0) c->set[1].loaded = false;  // a new row set serves as both until set 1 is loaded again
     return TAXI_OK;
 }
 

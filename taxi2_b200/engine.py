@@ -99,9 +99,10 @@ class Engine:
             data, off = pack_strings(seqs)
         N.check(self._lib.taxi_load_sequences(self._ctx, int(which), _p(data), _p(off), len(off) - 1))
         self.n[which] = len(off) - 1
-        if which == 0 and self.n[1] == 0:
+        if which == 0:  # a new row set serves as both until set 1 is loaded again
+            self.n[1] = 0
             self._y_is_x = True
-        if which == 1:
+        else:
             self._y_is_x = False
 
     @property

@@ -132,7 +132,6 @@ def test_sample_120_all_pairs(engine):
     n = len(seqs)
     engine.set_scores(None)
     engine.load(seqs, 0)
-    engine._y_is_x = True
     got = engine.align_rect(0, n, 0, n)
     from taxi2_b200.engine import pack_strings
 
