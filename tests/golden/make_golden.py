@@ -8,7 +8,8 @@ Sources (relative to /root/reference):
   tests/test_distances/metrics.tsv    -> metrics_cases.json (26 rows x 4 metrics, tol 5.1e-4)
   tests/test_distances.py:515-521     -> metrics_cases.json["exact"]
   tests/test_pairs/simple.*           -> pairs_simple.{tsv,formatted}
-  samples/Taxi2test1_{10,50,120}.tab  -> sample sequences for parity runs (ids + sequences only)
+  samples/Taxi2test1_{10,50,120}.tab  -> sample inputs for parity runs
+  tests/test_distances/*, tests/test_sequences/* (tsv, fas) -> distances/, sequences/ (handler fixtures)
 
 The reference test modules cannot be imported here (Bio / itaxotools.* are absent), so the
 tables are read with `ast` instead of being executed.
@@ -68,6 +69,19 @@ def metric_cases():
     return dict(tolerance=0.00051, labels=header[2:], rows=rows, exact=exact)
 
 
+def handler_fixtures():
+    """Data files of the reference's reader/writer tests for the formats either side of the path
+    (tests/test_distances/*, tests/test_sequences/* for Tabfile and Fasta only)."""
+    (OUT / "distances").mkdir(exist_ok=True)
+    (OUT / "sequences").mkdir(exist_ok=True)
+    for path in sorted((REF / "tests/test_distances").iterdir()):
+        if path.name != "metrics.tsv":
+            shutil.copyfile(path, OUT / "distances" / path.name)
+    for name in ("simple.tsv", "headers.tsv", "empty.tsv", "empty", "simple.fas", "simple.multi.fas", "simple.width.fas",
+                 "species.fas", "species.dot.fas", "alleles.concat.fas", "alleles.plain.fas", "alleles.species.fas"):
+        shutil.copyfile(REF / "tests/test_sequences" / name, OUT / "sequences" / name)
+
+
 def samples():
     for name in ("Taxi2test1_10", "Taxi2test1_50", "Taxi2test1_120"):
         shutil.copyfile(REF / "samples" / f"{name}.tab", OUT / f"{name}.tab")
@@ -79,4 +93,5 @@ if __name__ == "__main__":
     for name in ("simple.tsv", "simple.formatted"):
         shutil.copyfile(REF / "tests/test_pairs" / name, OUT / f"pairs_{name}")
     samples()
+    handler_fixtures()
     print("golden fixtures written to", OUT)
