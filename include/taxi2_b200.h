@@ -121,6 +121,15 @@ int taxi_count_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_
 int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
                             int32_t* out_index_host, double* out_value_host);
 
+/*
+ * Options: "force_general" = 1 routes every alignment through the general int32 kernel
+ * (the packed 16-bit fast path is only taken when it is provably exact for the score set and
+ * lengths; this switch exists so tests can compare the two).  taxi_last_kernel() reports which
+ * kernel the last alignment call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 (packed).
+ */
+int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
+int taxi_last_kernel(taxi_ctx* ctx);
+
 /* Telemetry of the last align call: kernels launched, DP cells, device milliseconds. */
 int taxi_last_stats(taxi_ctx* ctx, int64_t* launches, int64_t* cells, double* kernel_ms);
 

@@ -22,9 +22,19 @@ struct ScoreSet {
     int32_t pM, pX, pY;           // plain priorities (1..3)
 };
 
+// constants of the packed 16-bit fast path (gotoh_pair16.cuh), transformed score space, x16
+struct Fast16 {
+    int32_t D16;                       // (match - beta) * 16, <= 255 (the mismatch increment is 0)
+    int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties: internal open/extend, end open/extend
+    int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties
+    int32_t beta;                      // min(match, mismatch), unscaled
+};
+
 struct AlignArgs {
     const uint8_t* xb; const int64_t* xoff;   // row set (x): bytes + offsets
     const uint8_t* yb; const int64_t* yoff;   // column set (y)
+    const uint8_t* xc; const uint8_t* yc;     // 3-bit symbol codes (same offsets), fast path only
+    Fast16 f16;
     const int32_t* px; const int32_t* py;     // explicit pair list, or nullptr for rect mode
     int32_t x0, y0, ny;                       // rect mode: pair p = (x0 + p / ny, y0 + p % ny)
     long long npairs;

@@ -1,0 +1,305 @@
+// Fast path of the global affine-gap aligner: packed 16-bit DP, TWO pairs per warp.
+//
+// Same results as gotoh_warp.cuh (Biopython's first alignment + fused distance counts), for the
+// score sets and lengths where three simplifications are provably exact (checked on the host in
+// taxi_abi.cu: fast16_eligible()):
+//
+//  1. 16-bit cells.  Each 32-bit register holds the same DP cell of two different pairs (low
+//     half = pair A, high half = pair B), so every VIMNMX3/VIADDMNMX (.U16x2) advances two
+//     cells.  Values are kept unsigned around a bias of 0x8000 and in the transformed score
+//     space S' = S - beta*i (beta = min(match, mismatch)), which makes every diagonal increment
+//     non-negative and every gap step a non-negative penalty; plain 32-bit IADDs then never
+//     carry between the halves.
+//  2. Restricted recurrence.  When no co-optimal path can contain a vertical gap adjacent to a
+//     horizontal one (true for TaxI2's default scores; the host proves it per score set), the
+//     Ix<->Iy transitions of Biopython's recurrence can be dropped without changing the first
+//     alignment.  Ix and Iy then have two candidate predecessors instead of three.
+//  3. Tagged maxima with disjoint tag fields: candidates of H carry their priority in bits 0-1,
+//     the M-candidate of Ix sets bit 2, the M-candidate of Iy sets bit 3.  Ties resolve in
+//     Biopython's order (M before Ix before Iy) inside the max itself, and the 4-bit trace code
+//     of a cell is a single three-input OR of the values that arrive at it.
+//
+// Rows = x (<= 32*H, single stripe), lane l owns rows [l*H, l*H+H); columns stream one per step.
+#pragma once
+#include "common.cuh"
+
+namespace taxi {
+
+constexpr uint32_t F16_BIAS = 0x8000u;
+constexpr uint32_t F16_NEG = 0x0800u;          // "minus infinity": below every reachable value
+constexpr uint32_t F16_CLEAN = 0xFFF0FFF0u;
+
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
+
+__device__ __forceinline__ uint32_t lop3_or3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lop3_xor_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    // (a ^ b) | c : (0xF0 ^ 0xCC) | 0xAA = 0xBE
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(a), "r"(mask), "r"(c));
+    return r;
+}
+
+template <int H> struct Pair16Geom {
+    static constexpr int WORDS = (H + 1) / 2;                 // trace words per (lane, step): 2 rows x 2 pairs each
+    static constexpr int HB = (WORDS * 4 + 15) / 16 * 16;     // bytes per (lane, step)
+};
+
+// Warp-parallel first-path traceback over the 4-bit codes of one of the two pairs (half = 0/1).
+template <int H>
+__device__ __forceinline__ void traceback16(const AlignArgs& a, long long p, int lane, const uint8_t* trace, int half,
+                                            const uint8_t* __restrict__ x, const uint8_t* __restrict__ y,
+                                            int nA, int nB, int state, int score)
+{
+    constexpr int HB = Pair16Geom<H>::HB;
+    int i = nA, j = nB;
+    int same = 0, ts = 0, tv = 0, gapc = 0, pend = 0;
+    bool seen = false;
+    const bool strings = a.aln_x != nullptr;
+    int64_t wpos = strings ? a.aln_off[p + 1] : 0;
+    while (i > 0 && j > 0) {
+        const int di = (state != 2), dj = (state != 1);
+        const int ii = i - lane * di, jj = j - lane * dj;
+        const bool valid = ii >= 1 && jj >= 1;
+        int tb = 0, ca = 0, cb = 0;
+        if (valid) {
+            const int l = (ii - 1) / H, r = (ii - 1) % H;
+            tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l) * 32 + l) * HB + 2 * r + half);
+            ca = (int)__ldg(x + ii - 1);
+            cb = (int)__ldg(y + jj - 1);
+        }
+        // state I would hand over to if the path reaches my cell in `state`
+        int ns;
+        if (state == 0) ns = 3 - (tb & 3);            // 3 -> M, 2 -> Ix, 1 -> Iy
+        else if (state == 1) ns = (tb & 4) ? 0 : 1;   // Ix: opened from M, or extended
+        else ns = (tb & 8) ? 0 : 2;                   // Iy
+        const unsigned cont = __ballot_sync(TAXI_FULL_MASK, valid && ns == state);
+        const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, valid);
+        const int f = __ffs(~cont) - 1;
+        int V = (f < 0) ? 32 : f + 1;
+        V = min(V, __popc(vmask));
+        const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
+        const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
+        const int ka = (state == 2) ? 4 : base_class(ca);
+        const int kb = (state == 1) ? 4 : base_class(cb);
+        const bool both = ka < 4 && kb < 4;
+        const int d = ka ^ kb;
+        const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
+        const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
+        const unsigned tsm = __ballot_sync(TAXI_FULL_MASK, both && d == 1) & visited;
+        const unsigned tvm = __ballot_sync(TAXI_FULL_MASK, both && d > 1) & visited;
+        if (bm) {
+            ts += __popc(tsm); tv += __popc(tvm); same += __popc(bm & ~(tsm | tvm));
+            const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
+            const unsigned below = (1u << fb) - 1u;
+            const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
+            if (seen) gapc += pend + __popc(gm & below);
+            gapc += __popc(gm & upto & ~below);
+            pend = __popc(gm & ~upto);
+            seen = true;
+        } else {
+            pend += __popc(gm);
+        }
+        if (strings && lane < V) {
+            a.aln_x[wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
+            a.aln_y[wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
+        }
+        wpos -= V;
+        i -= V * di; j -= V * dj;
+        state = next;
+    }
+    if (strings) {
+        for (int k = lane; k < i; k += 32) { a.aln_x[wpos - 1 - k] = __ldg(x + i - 1 - k); a.aln_y[wpos - 1 - k] = '-'; }
+        wpos -= i;
+        for (int k = lane; k < j; k += 32) { a.aln_x[wpos - 1 - k] = '-'; a.aln_y[wpos - 1 - k] = __ldg(y + j - 1 - k); }
+        wpos -= j;
+        if (lane == 0) a.aln_start[p] = wpos;
+    }
+    if (lane != 0) return;
+    if (a.score) a.score[p] = score;
+    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);
+    if (a.metrics) {
+        double m[4];
+        metrics_from_counts(same, ts, tv, gapc, m);
+        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
+        dst[0] = make_double2(m[0], m[1]);
+        dst[1] = make_double2(m[2], m[3]);
+    }
+}
+
+struct PairRef {
+    const uint8_t* xb; const uint8_t* yb;   // ASCII (traceback classification / strings)
+    const uint8_t* xc; const uint8_t* yc;   // 3-bit codes (DP)
+    int nA, nB;
+};
+
+__device__ __forceinline__ PairRef pair_ref(const AlignArgs& a, long long p)
+{
+    int xi, yi;
+    if (a.px) { xi = a.px[p]; yi = a.py[p]; }
+    else { xi = a.x0 + (int)(p / a.ny); yi = a.y0 + (int)(p % a.ny); }
+    const int64_t xo = a.xoff[xi], yo = a.yoff[yi];
+    PairRef r;
+    r.xb = a.xb + xo; r.yb = a.yb + yo; r.xc = a.xc + xo; r.yc = a.yc + yo;
+    r.nA = (int)(a.xoff[xi + 1] - xo);
+    r.nB = (int)(a.yoff[yi + 1] - yo);
+    return r;
+}
+
+template <int H>
+__device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
+{
+    constexpr int HB = Pair16Geom<H>::HB;
+    constexpr int WORDS = Pair16Geom<H>::WORDS;
+    const Fast16& f = a.f16;
+    const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
+    const int nBmax = max(A.nB, B.nB), nAmax = max(A.nA, B.nA);
+    const int nlive = (nAmax + H - 1) / H;
+    const bool live = lane < nlive;
+    const int nsteps = nBmax + nlive - 1;
+    const int itop = lane * H + 1;
+
+    uint32_t a2[H], Hl[H], Yn[H], ncYM[H], cYY[H];
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+        const int i = itop + r;
+        const uint32_t c0 = (i <= A.nA) ? (uint32_t)__ldg(A.xc + min(i, A.nA) - 1) : 7u;
+        const uint32_t c1 = (i <= B.nA) ? (uint32_t)__ldg(B.xc + min(i, B.nA) - 1) : 7u;
+        a2[r] = c0 | (c1 << 8);
+        const uint32_t xb = F16_BIAS - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;   // Ix(i,0), tagged as state Ix
+        Hl[r] = pack16(xb, xb);
+        Yn[r] = pack16(F16_NEG, F16_NEG);                                        // no Ix->Iy: Iy(i,1) opens from M only
+        const int yo0 = (i == A.nA) ? f.PeoY : f.PoY, yo1 = (i == B.nA) ? f.PeoY : f.PoY;
+        const int ye0 = (i == A.nA) ? f.PeeY : f.PeY, ye1 = (i == B.nA) ? f.PeeY : f.PeY;
+        ncYM[r] = pack16((uint32_t)(5 - yo0), (uint32_t)(5 - yo1));   // M(tag 3) -> Iy candidate with bit 3 set
+        cYY[r] = pack16((uint32_t)(ye0 + 1), (uint32_t)(ye1 + 1));    // Iy(tag 1) -> Iy candidate with clean tag
+    }
+    uint32_t Hd_saved;
+    if (itop == 1) Hd_saved = pack16(F16_BIAS + 3u, F16_BIAS + 3u);   // (0,0): state M
+    else {
+        const uint32_t v = F16_BIAS - f.PeoX - (uint32_t)(itop - 2) * f.PeeX + 2u;
+        Hd_saved = pack16(v, v);
+    }
+    const int llA = (A.nA - 1) / H, rlA = (A.nA - 1) % H;
+    const int llB = (B.nA - 1) / H, rlB = (B.nA - 1) % H;
+    uint32_t outX = 0, outH = 0, finA = 0, finB = 0;
+    uint8_t* tbase = trace + (size_t)lane * HB;
+
+    // The sweep runs in up to three segments so that H(nA, nB) of each pair can be picked up
+    // right after the step that produces it (the other pair may keep the registers busy for
+    // more columns), without any capture logic inside the hot loop.
+    const int tA = A.nB - 1 + llA, tB = B.nB - 1 + llB;   // steps that produce the two end cells
+    int t = 0;
+#pragma unroll 1
+    for (int seg = 0; seg < 3; ++seg) {
+        const int tend = (seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps);
+        for (; t < tend; ++t) {
+            const int j = t - lane + 1;
+            uint32_t rX = __shfl_up_sync(TAXI_FULL_MASK, outX, 1);
+            uint32_t rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
+            const bool active = live && j >= 1 && j <= nBmax;
+            if (lane == 0 && active) {
+                // row 0: only Iy is alive (leading end gap); nothing can open Ix from it
+                const uint32_t y0 = F16_BIAS - f.PeoY - (uint32_t)(j - 1) * f.PeeY + 1u;
+                rH = pack16(y0, y0);
+                rX = pack16(F16_NEG, F16_NEG);
+            }
+            if (active) {
+                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : 7u;
+                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : 7u;
+                const uint32_t b2 = b0 | (b1 << 8);
+                const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
+                const int xe0 = (j == A.nB) ? f.PeeX : f.PeX, xe1 = (j == B.nB) ? f.PeeX : f.PeX;
+                const uint32_t ncXM = pack16((uint32_t)(1 - xo0), (uint32_t)(1 - xo1));  // M(tag 3) -> Ix candidate with bit 2 set
+                const uint32_t cXX = pack16((uint32_t)(xe0 + 2), (uint32_t)(xe1 + 2));   // Ix(tag 2) -> clean
+                uint32_t Hd = Hd_saved, Xin = rX;
+                uint32_t tw[WORDS];
+                uint32_t tprev = 0;
+#pragma unroll
+                for (int r = 0; r < H; ++r) {
+                    const uint32_t sel = lop3_xor_or(a2[r], b2, 0x7070u);
+                    const uint32_t sub = __byte_perm((uint32_t)f.D16, 0u, sel);   // (D16 or 0) per half
+                    const uint32_t Mr = Hd + sub;
+                    const uint32_t Yin = Yn[r];
+                    const uint32_t tc = lop3_or3(Mr, Xin, Yin);                   // 4-bit trace code per half (+ score bits above)
+                    const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
+                    const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
+                    const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
+                    Hd = Hl[r];
+                    Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
+                    Xin = __viaddmax_u16x2(Mt, ncXM, Xt - cXX);
+                    Yn[r] = __viaddmax_u16x2(Mt, ncYM[r], Yt - cYY[r]);
+                    if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
+                    else if (r == H - 1) tw[r >> 1] = __byte_perm(tc, 0u, 0x6420);
+                    tprev = tc;
+                }
+                outX = Xin;
+                outH = Hl[H - 1];
+                Hd_saved = rH;
+                uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+#pragma unroll
+                for (int k = 0; k < HB / 16; ++k) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[q] = (4 * k + q < WORDS) ? tw[4 * k + q] : 0u;
+                    __stcg(dst + k, make_uint4(w[0], w[1], w[2], w[3]));
+                }
+            }
+        }
+        if (t - 1 == tA && lane == llA) {
+#pragma unroll
+            for (int r = 0; r < H; ++r) finA = (r == rlA) ? (Hl[r] & 0xFFFFu) : finA;
+        }
+        if (t - 1 == tB && lane == llB) {
+#pragma unroll
+            for (int r = 0; r < H; ++r) finB = (r == rlB) ? (Hl[r] >> 16) : finB;
+        }
+    }
+    finA = __shfl_sync(TAXI_FULL_MASK, finA, llA);
+    finB = __shfl_sync(TAXI_FULL_MASK, finB, llB);
+    __syncwarp();
+
+    const int scoreA = ((int)(finA & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * A.nA;
+    traceback16<H>(a, p0, lane, trace, 0, A.xb, A.yb, A.nA, A.nB, 3 - (int)(finA & 3u), scoreA);
+    if (p1 != p0) {
+        const int scoreB = ((int)(finB & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * B.nA;
+        traceback16<H>(a, p1, lane, trace, 1, B.xb, B.yb, B.nA, B.nB, 3 - (int)(finB & 3u), scoreB);
+    }
+}
+
+constexpr int PAIR16_WARPS_PER_BLOCK = 4;
+
+template <int H>
+__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32)
+gotoh_pair16_kernel(const AlignArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * PAIR16_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    uint8_t* trace = a.trace + gw * a.trace_per_warp;
+    const unsigned long long units = ((unsigned long long)a.npairs + 1ULL) / 2ULL;
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(a.counter, 1ULL);
+        u = __shfl_sync(TAXI_FULL_MASK, u, 0);
+        if (u >= units) break;
+        const long long p0 = (long long)(2ULL * u);
+        const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
+        align_two<H>(a, p0, p1, lane, trace);
+        __syncwarp();
+    }
+}
+
+}  // namespace taxi

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "count_planes.cuh"
+#include "gotoh_pair16.cuh"
 #include "gotoh_warp.cuh"
 
 using namespace taxi;
@@ -60,6 +61,7 @@ struct SeqSet {
     int64_t total = 0;
     std::vector<int64_t> off;       // host copy of offsets
     DevBuf<uint8_t> bytes;          // normalized ASCII (DP kernels compare code points)
+    DevBuf<uint8_t> codes;          // 3-bit symbol codes for the packed fast path (valid if ctx->codebook_ok)
     DevBuf<int64_t> d_off;
     DevBuf<uint32_t> planes;        // [n][4][W]
     int32_t W = 0;
@@ -76,6 +78,14 @@ struct taxi_ctx {
     ScoreSet sc{};
     int32_t raw_scores[TAXI_NSCORES]{};
     bool have_scores = false;
+    // symbol codebook shared by both sets: A C G T N are fixed, up to two more symbols are
+    // assigned in order of appearance; more than 7 symbols disables the packed fast path
+    int16_t codebook[256];
+    int ncodes = 5;
+    bool codebook_ok = true;
+    DevBuf<uint8_t> d_codebook;
+    int force_general = 0;          // option: always use the general int32 kernel
+    int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
     DevBuf<uint8_t> trace;
     DevBuf<int32_t> bnd;
@@ -145,20 +155,98 @@ const Dispatch kDispatch[] = {
     {32, occupancy<32>, launch_gotoh<32>, TraceGeom<32>::HB},
 };
 
+// bytes -> 3-bit symbol codes through the context codebook (coalesced, one thread per 4 bytes)
+__global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, int64_t n, const uint8_t* __restrict__ book,
+                                    uint8_t* __restrict__ out)
+{
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x & 255] = book[threadIdx.x & 255];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = lut[bytes[k]];
+}
+
+template <int H> cudaError_t occupancy16(int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H>, PAIR16_WARPS_PER_BLOCK * 32, 0);
+}
+
+template <int H> void launch_pair16(const AlignArgs& a, int grid, cudaStream_t st)
+{
+    gotoh_pair16_kernel<H><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
+}
+
+const Dispatch kDispatch16[] = {
+    {8, occupancy16<8>, launch_pair16<8>, Pair16Geom<8>::HB},     {12, occupancy16<12>, launch_pair16<12>, Pair16Geom<12>::HB},
+    {16, occupancy16<16>, launch_pair16<16>, Pair16Geom<16>::HB}, {21, occupancy16<21>, launch_pair16<21>, Pair16Geom<21>::HB},
+    {24, occupancy16<24>, launch_pair16<24>, Pair16Geom<24>::HB}, {32, occupancy16<32>, launch_pair16<32>, Pair16Geom<32>::HB},
+};
+
+// Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
+bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out, int* H_out)
+{
+    if (c->force_general || !c->codebook_ok) return false;
+    const int32_t* s = c->raw_scores;
+    const int match = s[0], mm = s[1], io = s[2], ie = s[3], eo = s[4], ee = s[5];
+    if (io == ie && eo == ee) return false;                 // Needleman-Wunsch order: general kernel
+    if (match < mm) return false;
+    const int beta = mm, D = match - beta;
+    if (D * 16 > 255) return false;
+    // every gap step must be a non-negative penalty in the transformed space S' = S - beta*i
+    const int gaps[4] = {io, ie, eo, ee};
+    for (int g : gaps) if (g > beta || g > 0) return false;
+    // No co-optimal path may put a vertical gap next to a horizontal one: replacing runs
+    // (Iy^a Ix^b) by min(a,b) diagonals plus one gap of |a-b| must be strictly better for every
+    // a, b >= 1 and every end/internal typing of the two runs (worst case: all mismatches).
+    const int O[2] = {io, eo}, E[2] = {ie, ee};
+    for (int tx = 0; tx < 2; ++tx)
+        for (int ty = 0; ty < 2; ++ty) {
+            const int slope = E[tx] + E[ty] - beta;
+            if (slope > 0) return false;
+            if (O[tx] + E[ty] - beta >= 0) return false;     // a > b
+            if (O[ty] + E[tx] - beta >= 0) return false;     // b > a
+            if (O[tx] + O[ty] - beta >= 0) return false;     // a == b
+        }
+    // geometry: single stripe
+    int H = 0;
+    for (const auto& e : kDispatch16) if (32 * e.H >= max_rows) { H = e.H; break; }
+    if (!H) return false;
+    Fast16 f;
+    f.D16 = 16 * D; f.beta = beta;
+    f.PoX = 16 * (beta - io); f.PeX = 16 * (beta - ie); f.PeoX = 16 * (beta - eo); f.PeeX = 16 * (beta - ee);
+    f.PoY = -16 * io; f.PeY = -16 * ie; f.PeoY = -16 * eo; f.PeeY = -16 * ee;
+    // range: every value of the (padded) DP stays inside the unsigned 16-bit window around the bias
+    const long long R = 32LL * H, C = max_cols;
+    const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
+    const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
+    if (pen_o > 2000 || pen_e > 2000) return false;
+    const long long lower = 2 * pen_o + (R + C) * pen_e, upper = (long long)f.D16 * std::min(R, C);
+    if (0x8000LL - lower < 0x0800LL + 2 * 2048 || 0x8000LL + upper > 65000) return false;
+    *out = f; *H_out = H;
+    return true;
+}
+
 // Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
 // pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.
 int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
 {
-    const int H = pick_H(max_rows);
+    Fast16 f16{};
+    int H = 0;
+    const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H);
+    if (!fast) H = pick_H(max_rows);
     const Dispatch* d = nullptr;
-    for (const auto& e : kDispatch) if (e.H == H) d = &e;
+    if (fast) { for (const auto& e : kDispatch16) if (e.H == H) d = &e; }
+    else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
     int bps = 0;
     CUDA_TRY(d->occ(&bps));
     if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
     const long long SL = 32LL * H;
-    const long long nstripes = (max_rows + SL - 1) / SL;
+    const long long nstripes = fast ? 1 : (max_rows + SL - 1) / SL;
     const long long per_warp = ((nstripes * (max_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (max_cols + 2);
+    const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;
+    c->last_kernel = fast ? 16 : 32;
+    a.f16 = f16;
     // resident warps, capped by pairs and by a trace-arena budget of half the free memory
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -166,7 +254,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     const long long budget = (long long)((free_b + c->trace.cap) / 2);
     if (per_warp > budget) return fail(TAXI_E_NOMEM, "one pair needs %lld B of traceback arena, only %lld B available", per_warp, budget);
     warps = std::min(warps, std::max(1LL, budget / per_warp));
-    warps = std::min(warps, (a.npairs + 0LL));
+    warps = std::min(warps, work_units);
     int grid = (int)((warps + GOTOH_WARPS_PER_BLOCK - 1) / GOTOH_WARPS_PER_BLOCK);
     grid = std::max(grid, 1);
     const long long gw = (long long)grid * GOTOH_WARPS_PER_BLOCK;
@@ -216,6 +304,7 @@ void fill_rect(AlignArgs& a, const taxi_ctx* c, int32_t x0, int32_t y0, int32_t 
     const SeqSet& Y = yset(c);
     a.xb = X.bytes.p; a.xoff = X.d_off.p;
     a.yb = Y.bytes.p; a.yoff = Y.d_off.p;
+    a.xc = X.codes.p; a.yc = Y.codes.p;
     a.px = a.py = nullptr;
     a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
 }
@@ -336,7 +425,8 @@ void taxi_ctx_destroy(taxi_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : c->set) { s.bytes.release(); s.d_off.release(); s.planes.release(); }
+    for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); }
+    c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
     c->d_px.release(); c->d_py.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
@@ -386,6 +476,34 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
     CUDA_TRY(s.d_off.reserve((size_t)n + 1));
     if (s.total) CUDA_TRY(cudaMemcpyAsync(s.bytes.p, bytes, (size_t)s.total, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(s.d_off.p, s.off.data(), ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    // symbol codebook (host scan, O(total)); a new row set starts a new codebook
+    if (set == 0) {
+        for (auto& v : c->codebook) v = -1;
+        const char* fixed = "ACGTN";
+        for (int k = 0; k < 5; ++k) c->codebook[(unsigned char)fixed[k]] = (int16_t)k;
+        c->ncodes = 5;
+        c->codebook_ok = true;
+    }
+    for (int64_t k = 0; k < s.total && c->codebook_ok; ++k) {
+        if (c->codebook[bytes[k]] < 0) {
+            if (c->ncodes >= 7) c->codebook_ok = false;
+            else c->codebook[bytes[k]] = (int16_t)c->ncodes++;
+        }
+    }
+    if (c->codebook_ok) {
+        uint8_t book[256];
+        for (int k = 0; k < 256; ++k) book[k] = (uint8_t)(c->codebook[k] < 0 ? 7 : c->codebook[k]);
+        CUDA_TRY(c->d_codebook.reserve(256));
+        CUDA_TRY(cudaMemcpyAsync(c->d_codebook.p, book, 256, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // `book` is a stack buffer
+        CUDA_TRY(s.codes.reserve((size_t)s.total + 16));
+        if (s.total) {
+            encode_codes_kernel<<<(unsigned)std::min<int64_t>((s.total + 255) / 256, 4096), 256, 0, c->stream>>>(s.bytes.p, s.total, c->d_codebook.p, s.codes.p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        // a symbol first seen in set 1 extends the book: set 0 was encoded with the older book,
+        // which is still right for every symbol set 0 contains
+    }
     s.W = std::max(1, (s.maxlen + 31) / 32);
     CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * 4 * s.W));
     if (n > 0) {
@@ -611,6 +729,15 @@ int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, in
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return TAXI_OK;
 }
+
+int taxi_set_option(taxi_ctx* c, const char* key, int value)
+{
+    if (!c || !key) return fail(TAXI_E_ARG, "null argument");
+    if (std::strcmp(key, "force_general") == 0) { c->force_general = value; return TAXI_OK; }
+    return fail(TAXI_E_ARG, "unknown option %s", key);
+}
+
+int taxi_last_kernel(taxi_ctx* c) { return c ? c->last_kernel : 0; }
 
 int taxi_last_stats(taxi_ctx* c, int64_t* launches, int64_t* cells, double* kernel_ms)
 {

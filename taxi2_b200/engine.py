@@ -170,6 +170,14 @@ class Engine:
         N.check(self._lib.taxi_argmin_rows_device(self._ctx, C.c_void_p(d_metrics), nx, ny, metric, _p(idx), _p(val)))
         return idx, val
 
+    def set_option(self, key: str, value: int) -> None:
+        N.check(self._lib.taxi_set_option(self._ctx, key.encode(), int(value)))
+
+    @property
+    def last_kernel(self) -> int:
+        """32 = general int32 kernel, 16 = packed 16-bit two-pairs-per-warp kernel."""
+        return int(self._lib.taxi_last_kernel(self._ctx))
+
     def sync(self) -> None:
         N.check(self._lib.taxi_sync(self._ctx))
 

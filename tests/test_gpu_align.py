@@ -44,23 +44,37 @@ def oracle_batch(xs, ys, px, py, scores):
     return oracle.align_count_pairs(data, off, np.asarray(px), np.asarray(py) + len(xs), scores)
 
 
-def check_pairs(engine, xs, ys, scores, strings=True):
-    engine.set_scores(scores)
-    engine.load(xs, 0)
-    engine.load(ys, 1)
+def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
+    """Both kernels (packed 16-bit fast path where eligible, general int32) against the oracle."""
     n = len(xs)
     px = np.arange(n, dtype=np.int32)
-    got = engine.align_pairs(px, px)
     want = oracle_batch(xs, ys, px, px, scores)
-    assert np.array_equal(got["score"], want["score"])
-    assert np.array_equal(got["counts"], want["counts"])
-    assert_metrics_close(got["metrics"], want["metrics"])
-    if strings:
-        ax, ay, sc = engine.align_strings(px, px)
-        assert np.array_equal(sc, want["score"])
-        for k in range(n):
-            ox, oy, _ = oracle.align(xs[k], ys[k], scores)
-            assert ax[k].decode("latin-1") == ox and ay[k].decode("latin-1") == oy, (k, xs[k], ys[k])
+    kernels = set()
+    for force_general in (0, 1):
+        engine.set_option("force_general", force_general)
+        try:
+            engine.set_scores(scores)
+            engine.load(xs, 0)
+            engine.load(ys, 1)
+            got = engine.align_pairs(px, px)
+            kernels.add(engine.last_kernel)
+            if force_general:
+                assert engine.last_kernel == 32
+            assert np.array_equal(got["score"], want["score"])
+            assert np.array_equal(got["counts"], want["counts"])
+            assert_metrics_close(got["metrics"], want["metrics"])
+            if strings:
+                ax, ay, sc = engine.align_strings(px, px)
+                assert np.array_equal(sc, want["score"])
+                for k in range(n):
+                    ox, oy, _ = oracle.align(xs[k], ys[k], scores)
+                    assert ax[k].decode("latin-1") == ox and ay[k].decode("latin-1") == oy, (force_general, k, xs[k], ys[k])
+        finally:
+            engine.set_option("force_general", 0)
+    if expect_fast is True:
+        assert 16 in kernels, "packed fast path was expected to be eligible"
+    if expect_fast is False:
+        assert kernels == {32}
 
 
 @pytest.mark.parametrize("case", ALIGN["align_tests"] + ALIGN["align_tests_failing"],
@@ -99,7 +113,40 @@ def test_low_complexity_ties(engine):
 def test_barcode_length_pairs(engine):
     rng = np.random.default_rng(650)
     xs, ys = random_pairs(rng, 64, 560, 700, sub=0.12, indel=0.02)
-    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1))
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+    # odd pair count (last warp unit is half empty) and a score set that stays on the general kernel
+    check_pairs(engine, xs[:33], ys[:33], (1, -1, -8, -1, -1, -1), expect_fast=True)
+    check_pairs(engine, xs[:8], ys[:8], (1, 0, 0, 0, 0, 0), expect_fast=False)
+
+
+def test_fast_path_score_sets(engine):
+    """Score sets that satisfy the fast-path proof obligations, on tie-rich low-complexity input."""
+    rng = np.random.default_rng(16)
+    xs, ys = random_pairs(rng, 300, 1, 120, sub=0.2, indel=0.06, alphabet=b"ACGTN")
+    xs2, ys2 = random_pairs(rng, 300, 1, 120, sub=0.3, indel=0.1, alphabet=b"AT")
+    for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (5, -4, -10, -4, -4, -4), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2)]:
+        check_pairs(engine, xs, ys, scores, expect_fast=True)
+        check_pairs(engine, xs2, ys2, scores, expect_fast=True)
+
+
+def test_mixed_lengths_in_one_warp(engine):
+    """Neighbouring pairs of very different lengths share a warp in the packed kernel."""
+    rng = np.random.default_rng(99)
+    xs, ys = [], []
+    for k in range(120):
+        lo, hi = (5, 40) if k % 3 == 0 else ((300, 420) if k % 3 == 1 else (600, 700))
+        x, y = random_pairs(rng, 1, lo, hi, sub=0.15, indel=0.03)
+        xs += x; ys += y
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+
+
+def test_extra_symbols(engine):
+    """IUPAC symbols: up to seven distinct symbols stay on the fast path, more fall back."""
+    rng = np.random.default_rng(5)
+    xs, ys = random_pairs(rng, 60, 20, 150, alphabet=b"ACGTNRY")
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+    xs, ys = random_pairs(rng, 60, 20, 150, alphabet=b"ACGTNRYKMSW")
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=False)
 
 
 def test_multi_stripe_long_pairs(engine):
