@@ -447,7 +447,7 @@ int taxi_set_scores(taxi_ctx* c, const int32_t s[TAXI_NSCORES])
     sc.match = s[0] * 64; sc.mismatch = s[1] * 64;
     sc.io = s[2] * 64; sc.ie = s[3] * 64; sc.eo = s[4] * 64; sc.ee = s[5] * 64;
     // Biopython picks Needleman-Wunsch when every open == extend, else Gotoh; their path
-    // generators visit co-optimal predecessors in different orders (see oracle/taxi_oracle.c).
+    // generators visit co-optimal predecessors in different orders ("tie-breaking").
     const bool gotoh = !(s[2] == s[3] && s[4] == s[5]);
     if (gotoh) { sc.pM = 3; sc.pX = 2; sc.pY = 1; }
     else       { sc.pM = 1; sc.pX = 2; sc.pY = 3; }
