@@ -282,7 +282,7 @@ def main() -> None:
         ys = (data[off[y0]:off[y0 + TILE_Y]], off[y0:y0 + TILE_Y + 1] - off[y0])
         eng2.load(xs, 0)
         eng2.load(ys, 1)
-        out = eng2.align_rect(0, TILE_X, 0, TILE_Y, want=("counts", "metrics"))
+        out = eng2.align_rect(0, TILE_X, 0, TILE_Y, want=("counts", "metrics"), pinned=True)
         h2d = xs[0].nbytes + xs[1].nbytes + ys[0].nbytes + ys[1].nbytes
         d2h = out["counts"].nbytes + out["metrics"].nbytes
 

@@ -122,6 +122,13 @@ int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, 
                             int32_t* out_index_host, double* out_value_host);
 
 /*
+ * Page-locked host buffers for the host-facing calls above: results land in them with an
+ * asynchronous DMA instead of a staged pageable copy.  Plain malloc'ed buffers work too.
+ */
+void* taxi_host_alloc(int64_t bytes);
+void taxi_host_free(void* p);
+
+/*
  * Options: "force_general" = 1 routes every alignment through the general int32 kernel
  * (the packed 16-bit fast path is only taken when it is provably exact for the score set and
  * lengths; this switch exists so tests can compare the two).  taxi_last_kernel() reports which

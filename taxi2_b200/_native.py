@@ -47,6 +47,8 @@ SIGNATURES = {
     "taxi_count_rect_device": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "taxi_count_pairs": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "taxi_argmin_rows_device": (C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "taxi_host_alloc": (C.c_void_p, [C.c_int64]),
+    "taxi_host_free": (None, [C.c_void_p]),
     "taxi_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int]),
     "taxi_last_kernel": (C.c_int, [_ctx]),
     "taxi_last_stats": (C.c_int, [_ctx, _i64p, _i64p, _f64p]),

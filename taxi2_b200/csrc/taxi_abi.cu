@@ -730,6 +730,16 @@ int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, in
     return TAXI_OK;
 }
 
+void* taxi_host_alloc(int64_t bytes)
+{
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail(TAXI_E_NOMEM, "cudaHostAlloc(%lld) failed", (long long)bytes); return nullptr; }
+    return p;
+}
+
+void taxi_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int taxi_set_option(taxi_ctx* c, const char* key, int value)
 {
     if (!c || !key) return fail(TAXI_E_ARG, "null argument");

@@ -54,6 +54,27 @@ def _p(a: np.ndarray | None):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class PinnedArray:
+    """numpy view of a page-locked host buffer owned by the library (freed with the object)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = N.load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = self._lib.taxi_host_alloc(max(self.nbytes, 1))
+        if not self._ptr:
+            raise MemoryError("taxi_host_alloc failed")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ptr", None):
+                self._lib.taxi_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 class Engine:
     """One GPU context.  Not thread-safe; create one per device (one process per GPU)."""
 
@@ -63,6 +84,7 @@ class Engine:
         N.check(self._lib.taxi_ctx_create(int(device), C.byref(self._ctx)))
         self.device = int(device)
         self.n = [0, 0]
+        self._pinned_pool: dict = {}
         self.set_scores(scores)
 
     # -- lifecycle ---------------------------------------------------------------------------
@@ -110,9 +132,11 @@ class Engine:
         return self.n[0] if getattr(self, "_y_is_x", True) else self.n[1]
 
     # -- aligned path ------------------------------------------------------------------------
-    def align_rect(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics")) -> dict:
+    def align_rect(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics"), pinned: bool = False) -> dict:
+        """pinned=True reuses page-locked result buffers owned by the engine: the returned arrays are
+        views that the next pinned call overwrites."""
         npairs = nx * ny
-        flags, score, counts, metrics = self._outputs(npairs, want)
+        flags, score, counts, metrics = self._outputs(npairs, want, self._pinned_pool if pinned else None)
         N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, (nx, ny))
 
@@ -188,18 +212,26 @@ class Engine:
 
     # -- helpers -----------------------------------------------------------------------------
     @staticmethod
-    def _outputs(n: int, want: Seq[str]):
+    def _outputs(n: int, want: Seq[str], pool: dict | None = None):
+        def buffer(key, shape, dtype):
+            if pool is None:
+                return np.zeros(shape, dtype=dtype)
+            held = pool.get(key)
+            if held is None or held.array.shape[0] < shape[0]:
+                held = pool[key] = PinnedArray(shape, dtype)
+            return held.array[: shape[0]]
+
         flags = 0
         score = counts = metrics = None
         if "score" in want:
             flags |= N.OUT_SCORE
-            score = np.zeros(max(n, 1), dtype=np.int32)[:n]
+            score = buffer("score", (max(n, 1),), np.int32)[:n]
         if "counts" in want:
             flags |= N.OUT_COUNTS
-            counts = np.zeros((max(n, 1), 4), dtype=np.int32)[:n]
+            counts = buffer("counts", (max(n, 1), 4), np.int32)[:n]
         if "metrics" in want:
             flags |= N.OUT_METRICS
-            metrics = np.full((max(n, 1), 4), np.nan, dtype=np.float64)[:n]
+            metrics = buffer("metrics", (max(n, 1), 4), np.float64)[:n]
         return flags, score, counts, metrics
 
     @staticmethod

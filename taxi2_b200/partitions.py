@@ -1,0 +1,83 @@
+"""Partitions (individual id -> subset) as far as the distance tasks need them.
+
+Mirrors /root/reference/src/itaxotools/taxi2/partitions.py:15-110 for the tabular formats; the
+Spart / Fasta / Excel partition readers are out of scope (metadata join, not on the compute path).
+"""
+from __future__ import annotations
+
+from abc import abstractmethod
+from pathlib import Path
+from typing import Callable, Literal, NamedTuple
+
+from .handlers import FileHandler, ReadHandle, WriteHandle
+
+
+class Classification(NamedTuple):
+    individual: str
+    subset: str
+
+
+class Partition(dict):
+    """Keys are individuals, values are subsets"""
+
+    @classmethod
+    def fromPath(cls, path: Path, handler: "PartitionHandler", *args, **kwargs) -> "Partition":
+        return handler.as_dict(path, *args, **kwargs)
+
+
+class PartitionHandler(FileHandler[Classification]):
+    @classmethod
+    def as_dict(cls, path: Path, *args, **kwargs) -> Partition:
+        partition = Partition()
+        for individual, subset in cls(path, "r", *args, **kwargs):
+            partition[individual] = subset
+        return partition
+
+    def _open(self, path: Path, mode: Literal["r", "w"] = "r", filter: Callable = None, *args, **kwargs):
+        self.filter = filter
+        super()._open(path, mode, *args, **kwargs)
+
+    def _iter_write(self) -> WriteHandle[Classification]:
+        raise NotImplementedError()
+
+    def _iter_read(self, *args, **kwargs) -> ReadHandle[Classification]:
+        inner = self._iter_read_inner(*args, **kwargs)
+        yield next(inner)
+        for classification in inner:
+            if self.filter:
+                classification = self.filter(classification)
+            if classification is not None:
+                yield classification
+
+    @abstractmethod
+    def _iter_read_inner(self, *args, **kwargs) -> ReadHandle[Classification]:
+        yield self
+
+    @staticmethod
+    def subset_first_word(classification: Classification) -> Classification | None:
+        """Genus = first word of the organism column (partitions.py:67-75)."""
+        individual, subset = classification
+        first, sep, _ = subset.partition(" ")
+        if not sep:
+            print(f"Cannot split subset {subset} for individual {individual}")
+            return None
+        return Classification(individual, first)
+
+
+class Tabular(PartitionHandler):
+    subhandler = FileHandler.Tabular
+
+    def _iter_read_inner(self, idHeader: str = None, subHeader: str = None, hasHeader: bool = False,
+                         idColumn: int = 0, subColumn: int = 1) -> ReadHandle[Classification]:
+        if idHeader and subHeader:
+            columns, hasHeader = (idHeader, subHeader), True
+        else:
+            columns = (idColumn, subColumn)
+        with self.subhandler(self.path, has_headers=hasHeader, columns=columns) as rows:
+            yield self
+            for individual, subset in rows:
+                yield Classification(individual, subset)
+
+
+class Tabfile(Tabular, PartitionHandler):
+    subhandler = FileHandler.Tabular.Tabfile

@@ -1,0 +1,318 @@
+"""VersusAll: every sequence against every sequence (full ordered N x N product, diagonal
+included), alignment + the selected metrics, with the reference's output files.
+
+Mirrors /root/reference/src/itaxotools/taxi2/tasks/versus_all.py (attribute surface :374-415,
+pipeline :732-773, writers :98-350).  Differences, all out of the hot-path scope:
+per-sequence statistics files (stats/*.tsv) and histogram plots are not produced.
+"""
+from __future__ import annotations
+
+from itertools import chain, product
+from math import inf
+from pathlib import Path
+from time import perf_counter
+from typing import Callable, Iterator, NamedTuple
+
+import numpy as np
+
+from ..align import Scores
+from ..distances import Distance, DistanceHandler, DistanceMetric
+from ..handlers import FileHandler
+from ..pairs import SequencePair, SequencePairHandler
+from ..sequences import Sequence, Sequences
+from ..types import AttrDict
+from .common import ComparisonType, Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none
+
+
+class SimpleAggregator:
+    """Running sum / min / max / n of the defined distances (versus_all.py:57-77);
+    max starts at 0.0 and min at +inf exactly like the reference."""
+
+    def __init__(self):
+        self.sum, self.min, self.max, self.n = 0.0, inf, 0.0, 0
+
+    def add(self, value: float | None) -> None:
+        if value is None:
+            return
+        self.sum += value
+        self.min = min(self.min, value)
+        self.max = max(self.max, value)
+        self.n += 1
+
+    def calculate(self):
+        if not self.n:
+            return (None, None, None, 0)
+        return (self.min, self.max, self.sum / self.n, self.n)
+
+
+class DistanceStatistics(NamedTuple):
+    metric: DistanceMetric
+    idx: str
+    idy: str
+    min: float
+    max: float
+    mean: float
+    count: int
+
+
+class DistanceAggregator:
+    def __init__(self, metric: DistanceMetric):
+        self.metric = metric
+        self.aggs: dict = {}
+
+    def add(self, idx, idy, d) -> None:
+        agg = self.aggs.get((idx, idy))
+        if agg is None:
+            agg = self.aggs[(idx, idy)] = SimpleAggregator()
+        agg.add(d)
+
+    def __iter__(self) -> Iterator[DistanceStatistics]:
+        for (idx, idy), agg in self.aggs.items():
+            mn, mx, mean, n = agg.calculate()
+            yield DistanceStatistics(self.metric, idx, idy, mn, mx, mean, n)
+
+
+COMPARISON = {
+    (None, None): ComparisonType.Unknown,
+    (None, True): ComparisonType.IntraSpecies,
+    (None, False): ComparisonType.InterSpecies,
+    (False, None): ComparisonType.InterGenus,
+    (False, True): ComparisonType.InterGenus,
+    (False, False): ComparisonType.InterGenus,
+    (True, None): ComparisonType.IntraGenus,
+    (True, True): ComparisonType.IntraSpecies,
+    (True, False): ComparisonType.InterSpecies,
+}
+
+
+class VersusAll:
+    def __init__(self):
+        self.work_dir: Path = None
+        self.paths = AttrDict()
+        self.progress_handler: Callable = console_report
+        self.progress_interval: float = 0.015
+        self.device: int = 0
+
+        self.input = AttrDict()
+        self.input.sequences: Sequences = None
+        self.input.species = None
+        self.input.genera = None
+
+        self.params = AttrDict()
+        self.params.pairs = AttrDict(align=True, write=True, scores=None)
+        self.params.distances = AttrDict(metrics=None, write_linear=True, write_matricial=True)
+        self.params.plot = AttrDict(histograms=True, binwidth=0.05, formats=None, palette=None)
+        self.params.format = AttrDict(float="{:.4f}", percentage="{:.2f}", missing="NA",
+                                      stats_template="{mean} ({min}-{max})", percentage_multiply=False)
+        self.params.stats = AttrDict(all=True, species=True, genera=True)
+
+    # -- paths / parameters (versus_all.py:417-446) -----------------------------------------------
+    def generate_paths(self):
+        assert self.work_dir
+        w = Path(self.work_dir)
+        self.paths.summary = w / "summary.tsv"
+        self.paths.aligned_pairs = w / "align" / "aligned_pairs.txt"
+        self.paths.distances_linear = w / "distances" / "linear.tsv"
+        self.paths.distances_matricial = w / "distances" / "matricial"
+        self.paths.subsets = w / "subsets"
+        create_parents(self.paths.summary)
+
+    def check_metrics(self):
+        self.params.distances.metrics = self.params.distances.metrics or [
+            DistanceMetric.Uncorrected(), DistanceMetric.UncorrectedWithGaps(),
+            DistanceMetric.JukesCantor(), DistanceMetric.Kimura2P()]
+
+    # -- the run -----------------------------------------------------------------------------------
+    def start(self) -> Results:
+        from ..engine import default_engine
+
+        ts = perf_counter()
+        self.generate_paths()
+        self.check_metrics()
+        p = self.params
+        metrics = p.distances.metrics
+        columns = metric_columns(metrics)
+        fmt, missing = p.format.float, p.format.missing
+        scale = 100.0 if p.format.percentage_multiply else 1.0
+
+        sequences = list(self.input.sequences.normalize() if p.pairs.align else self.input.sequences)
+        n = len(sequences)
+        engine = default_engine(self.device)
+
+        writers = []
+        pairs_file = linear_file = None
+        matrix_files = []
+        if p.pairs.align and p.pairs.write:
+            create_parents(self.paths.aligned_pairs)
+            pairs_file = SequencePairHandler.Formatted(self.paths.aligned_pairs, "w")
+            writers.append(pairs_file)
+        if p.distances.write_linear:
+            create_parents(self.paths.distances_linear)
+            linear_file = DistanceHandler.Linear.WithExtras(self.paths.distances_linear, "w", missing=missing, formatter=fmt)
+            writers.append(linear_file)
+        if p.distances.write_matricial:
+            create_parents(self.paths.distances_matricial / "x.tsv")
+            for metric in metrics:
+                f = DistanceHandler.Matrix(self.paths.distances_matricial / f"{metric}.tsv", "w", missing=missing, formatter=fmt)
+                matrix_files.append(f)
+                writers.append(f)
+        summary = SummaryWriter(self.paths.summary, missing, fmt)
+        agg_species = SubsetAggregation(self.input.species, metrics) if self.input.species else None
+        agg_genera = SubsetAggregation(self.input.genera, metrics) if self.input.genera else None
+
+        total = len(metrics) * n * n
+        done, last_time = 0, perf_counter()
+        try:
+            for block in iter_pair_blocks(engine, sequences, None, p.pairs.align, pairs_file is not None, p.pairs.scores):
+                for bx in range(block.nx):
+                    x = sequences[block.x0 + bx]
+                    for j in range(n):
+                        y = sequences[j]
+                        if block.aligned is not None:
+                            ax, ay = block.aligned[bx * n + j]
+                            pair = SequencePair(Sequence(x.id, ax, x.extras), Sequence(y.id, ay, y.extras))
+                            pairs_file.write(pair)
+                        else:
+                            pair = SequencePair(x, y)
+                        undefined = self._same_record(engine, block.x0 + bx, j, x, y, pair, p.pairs.align, block.aligned is not None)
+                        row = []
+                        for metric, col in zip(metrics, columns):
+                            d = None if undefined else number_or_none(block.metrics[bx, j, col])
+                            if d is not None:
+                                d *= scale
+                            row.append(Distance(metric, pair.x, pair.y, d))
+                        for k, distance in enumerate(row):
+                            if linear_file:
+                                linear_file.write(distance)
+                            if matrix_files:
+                                matrix_files[k].write(distance)
+                        gen = agg_genera.add(row) if agg_genera else None
+                        spe = agg_species.add(row) if agg_species else None
+                        summary.write(row, gen, spe)
+                        done += len(row)
+                        now = perf_counter()
+                        if now - last_time >= self.progress_interval:
+                            self.progress_handler("distance.x.id", done, total)
+                            last_time = now
+            self.progress_handler("Finalizing...", total, total)
+        finally:
+            for w in writers:
+                w.close()
+            summary.close()
+        if agg_genera:
+            agg_genera.write(self.paths.subsets / "genera", p.format)
+        if agg_species:
+            agg_species.write(self.paths.subsets / "species", p.format)
+        return Results(self.work_dir, perf_counter() - ts)
+
+    @staticmethod
+    def _same_record(engine, i: int, j: int, x: Sequence, y: Sequence, pair: SequencePair, aligned: bool, have_strings: bool) -> bool:
+        """versus_all.py:549-552: distances are None when the two (aligned) records compare equal as
+        tuples.  Equal aligned strings imply equal raw strings, so only candidates with identical
+        id / sequence / extras need the alignment itself (one extra single-pair launch each)."""
+        if x.id != y.id or x.seq != y.seq or x.extras != y.extras:
+            return False
+        if not aligned:
+            return True
+        if have_strings:
+            return pair.x == pair.y
+        ax, ay, _ = engine.align_strings([i], [j])   # indices into the loaded set (it serves both sides)
+        return ax[0] == ay[0]
+
+
+class SubsetAggregation:
+    """Per (subset_x, subset_y) statistics of every metric (versus_all.py:623-684)."""
+
+    def __init__(self, partition, metrics):
+        self.partition = partition
+        self.aggregators = {str(m): DistanceAggregator(m) for m in metrics}
+
+    def add(self, row: list[Distance]):
+        sx = self.partition.get(row[0].x.id, None)
+        sy = self.partition.get(row[0].y.id, None)
+        for d in row:
+            self.aggregators[str(d.metric)].add(sx, sy, d.d)
+        return (sx, sy)
+
+    def write(self, path: Path, fmt) -> None:
+        # the subset writers of the reference keep their own default missing marker "NA"
+        to_text = lambda v: "NA" if v is None else fmt.float.format(v)  # noqa: E731
+        linear = path / "linear"
+        linear.mkdir(parents=True, exist_ok=True)
+        with FileHandler.Tabfile(linear / "pairs.tsv", "w") as pairs_file, \
+                FileHandler.Tabfile(linear / "identity.tsv", "w") as identity_file:
+            wrote = {"pairs": False, "identity": False}
+            for bunch in zip(*(iter(a) for a in self.aggregators.values())):
+                names = [f"{s.metric} {stat}" for s, stat in product(bunch, ["mean", "min", "max"])]
+                values = [to_text(v) for v in chain(*((s.mean, s.min, s.max) for s in bunch))]
+                idx = "?" if bunch[0].idx is None else bunch[0].idx
+                idy = "?" if bunch[0].idy is None else bunch[0].idy
+                if bunch[0].idx == bunch[0].idy:
+                    if not wrote["identity"]:
+                        identity_file.write(("target", *names))
+                        wrote["identity"] = True
+                    identity_file.write((idx, *values))
+                else:
+                    if not wrote["pairs"]:
+                        pairs_file.write(("target", "query", *names))
+                        wrote["pairs"] = True
+                    pairs_file.write((idx, idy, *values))
+        matricial = path / "matricial"
+        matricial.mkdir(parents=True, exist_ok=True)
+        for label, aggregator in self.aggregators.items():
+            with FileHandler.Tabfile(matricial / f"{label}.tsv", "w") as file:
+                line: list[DistanceStatistics] = []
+                wrote_header = False
+
+                def flush():
+                    nonlocal wrote_header
+                    if not wrote_header:
+                        file.write(("", *("?" if s.idy is None else s.idy for s in line)))
+                        wrote_header = True
+                    cells = []
+                    for s in line:
+                        if not s.count:
+                            cells.append("NA")
+                        else:
+                            cells.append(fmt.stats_template.format(mean=to_text(s.mean), min=to_text(s.min), max=to_text(s.max)))
+                    file.write(("?" if line[0].idx is None else line[0].idx, *cells))
+
+                for stats in aggregator:
+                    if line and line[0].idx != stats.idx:
+                        flush()
+                        line = []
+                    line.append(stats)
+                if line:
+                    flush()
+
+
+class SummaryWriter:
+    """summary.tsv (versus_all.py:278-350): ids, metrics, extras of both records, genus / species
+    of both, and the comparison type."""
+
+    def __init__(self, path: Path, missing: str, formatter: str):
+        self.file = FileHandler.Tabfile(path, "w")
+        self.missing, self.formatter = missing, formatter
+        self.wrote_headers = False
+        self.tagX, self.tagY = " (query 1)", " (query 2)"
+
+    def write(self, row: list[Distance], genera, species) -> None:
+        x, y = row[0].x, row[0].y
+        if not self.wrote_headers:
+            self.file.write(("seqid" + self.tagX, "seqid" + self.tagY, *(str(d.metric) for d in row),
+                             *(k + self.tagX for k in x.extras), *(k + self.tagY for k in y.extras),
+                             "genus" + self.tagX, "species" + self.tagX, "genus" + self.tagY, "species" + self.tagY,
+                             "comparison_type"))
+            self.wrote_headers = True
+        same_genera = bool(genera[0] == genera[1]) if genera else None
+        same_species = bool(species[0] == species[1]) if species else None
+        fill = lambda values: [self.missing if v is None else v for v in values]  # noqa: E731
+        self.file.write((x.id, y.id,
+                         *(self.missing if d.d is None else self.formatter.format(d.d) for d in row),
+                         *fill(x.extras.values()), *fill(y.extras.values()),
+                         (genera[0] if genera else "-") or "-", (species[0] if species else "-") or "-",
+                         (genera[1] if genera else "-") or "-", (species[1] if species else "-") or "-",
+                         COMPARISON[(same_genera, same_species)].label))
+
+    def close(self) -> None:
+        self.file.close()

@@ -1,0 +1,174 @@
+"""Per-pair restatement of the reference's task pipelines for the parity tests (test
+infrastructure): the same generator order as /root/reference/src/itaxotools/taxi2/tasks/
+versus_all.py:732-773 and versus_reference.py:213-247, with the two native calls answered by the
+CPU oracle.  Deliberately written pair-at-a-time, independent of taxi2_b200.tasks."""
+from __future__ import annotations
+
+from itertools import groupby
+from math import inf, isnan
+from pathlib import Path
+
+import oracle
+from taxi2_b200.distances import Distance, DistanceHandler, DistanceMetric
+from taxi2_b200.handlers import FileHandler
+from taxi2_b200.pairs import SequencePair, SequencePairHandler
+from taxi2_b200.sequences import Sequence
+
+LABELS = ["p", "p-gaps", "jc", "k2p"]
+
+
+def oracle_metric(metric, x: Sequence, y: Sequence):
+    c = oracle.count(x.seq, y.seq)
+    if c is None:
+        return None
+    v = oracle.metrics(c)[LABELS.index(str(metric))]
+    return None if isnan(v) else v
+
+
+def oracle_align(pair: SequencePair, scores=None) -> SequencePair:
+    ax, ay, _ = oracle.align(pair.x.seq, pair.y.seq, scores)
+    return SequencePair(Sequence(pair.x.id, ax, pair.x.extras), Sequence(pair.y.id, ay, pair.y.extras))
+
+
+COMPARISON = {(None, None): "no info", (None, True): "intra-species", (None, False): "inter-species",
+              (False, None): "inter-genus", (False, True): "inter-genus", (False, False): "inter-genus",
+              (True, None): "intra-genus", (True, True): "intra-species", (True, False): "inter-species"}
+
+
+def versus_all(sequences, work: Path, species=None, genera=None, align=True, metrics=None, fmt="{:.4f}", missing="NA",
+               multiply=False):
+    metrics = metrics or [DistanceMetric.fromLabel(label) for label in LABELS]
+    work = Path(work)
+    (work / "align").mkdir(parents=True, exist_ok=True)
+    (work / "distances" / "matricial").mkdir(parents=True, exist_ok=True)
+    seqs = [s.normalize() for s in sequences] if align else list(sequences)
+    text = lambda v: missing if v is None else fmt.format(v)  # noqa: E731
+    aggs = {name: {str(m): {} for m in metrics} for name in ("genera", "species")}
+    with SequencePairHandler.Formatted(work / "align" / "aligned_pairs.txt", "w") as pairs_file, \
+            DistanceHandler.Linear.WithExtras(work / "distances" / "linear.tsv", "w", missing=missing, formatter=fmt) as linear, \
+            FileHandler.Tabfile(work / "summary.tsv", "w") as summary:
+        matrices = [DistanceHandler.Matrix(work / "distances" / "matricial" / f"{m}.tsv", "w", missing=missing, formatter=fmt) for m in metrics]
+        wrote_summary_header = False
+        for x in seqs:
+            for y in seqs:
+                pair = SequencePair(x, y)
+                if align:
+                    pair = oracle_align(pair)
+                    pairs_file.write(pair)
+                row = []
+                for metric in metrics:
+                    d = oracle_metric(metric, pair.x, pair.y) if pair.x != pair.y else None
+                    if d is not None and multiply:
+                        d *= 100
+                    row.append(Distance(metric, pair.x, pair.y, d))
+                for k, d in enumerate(row):
+                    linear.write(d)
+                    matrices[k].write(d)
+                subset = {}
+                for name, part in (("genera", genera), ("species", species)):
+                    if part is None:
+                        subset[name] = None
+                        continue
+                    sx, sy = part.get(x.id, None), part.get(y.id, None)
+                    subset[name] = (sx, sy)
+                    for d in row:
+                        a = aggs[name][str(d.metric)].setdefault((sx, sy), [0.0, inf, 0.0, 0])
+                        if d.d is not None:
+                            a[0] += d.d; a[1] = min(a[1], d.d); a[2] = max(a[2], d.d); a[3] += 1
+                if not wrote_summary_header:
+                    summary.write(("seqid (query 1)", "seqid (query 2)", *(str(m) for m in metrics),
+                                   *(k + " (query 1)" for k in pair.x.extras), *(k + " (query 2)" for k in pair.y.extras),
+                                   "genus (query 1)", "species (query 1)", "genus (query 2)", "species (query 2)", "comparison_type"))
+                    wrote_summary_header = True
+                g, s = subset["genera"], subset["species"]
+                same_g = bool(g[0] == g[1]) if g else None
+                same_s = bool(s[0] == s[1]) if s else None
+                summary.write((pair.x.id, pair.y.id, *(text(d.d) for d in row),
+                               *(missing if v is None else v for v in pair.x.extras.values()),
+                               *(missing if v is None else v for v in pair.y.extras.values()),
+                               (g[0] if g else "-") or "-", (s[0] if s else "-") or "-",
+                               (g[1] if g else "-") or "-", (s[1] if s else "-") or "-", COMPARISON[(same_g, same_s)]))
+        for m in matrices:
+            m.close()
+    if not align:
+        (work / "align" / "aligned_pairs.txt").unlink()
+        (work / "align").rmdir()
+    for name, part in (("genera", genera), ("species", species)):
+        if part is None:
+            continue
+        base = work / "subsets" / name
+        (base / "linear").mkdir(parents=True, exist_ok=True)
+        (base / "matricial").mkdir(parents=True, exist_ok=True)
+        stat = lambda a: (None, None, None) if not a[3] else (a[0] / a[3], a[1], a[2])  # noqa: E731  mean, min, max
+        ftext = lambda v: "NA" if v is None else fmt.format(v)  # noqa: E731
+        keys = list(next(iter(aggs[name].values())).keys())
+        with FileHandler.Tabfile(base / "linear" / "pairs.tsv", "w") as pf, FileHandler.Tabfile(base / "linear" / "identity.tsv", "w") as idf:
+            heads = [f"{m} {s}" for m in metrics for s in ("mean", "min", "max")]
+            wrote = [False, False]
+            for key in keys:
+                vals = [ftext(v) for m in metrics for v in stat(aggs[name][str(m)][key])]
+                q = lambda v: "?" if v is None else v  # noqa: E731
+                if key[0] == key[1]:
+                    if not wrote[0]:
+                        idf.write(("target", *heads)); wrote[0] = True
+                    idf.write((q(key[0]), *vals))
+                else:
+                    if not wrote[1]:
+                        pf.write(("target", "query", *heads)); wrote[1] = True
+                    pf.write((q(key[0]), q(key[1]), *vals))
+        for m in metrics:
+            with FileHandler.Tabfile(base / "matricial" / f"{m}.tsv", "w") as f:
+                rows = [(k, list(grp)) for k, grp in groupby(keys, key=lambda kk: kk[0])]
+                header_done = False
+                for idx, grp in rows:
+                    if not header_done:
+                        f.write(("", *("?" if k[1] is None else k[1] for k in grp))); header_done = True
+                    cells = []
+                    for k in grp:
+                        a = aggs[name][str(m)][k]
+                        if not a[3]:
+                            cells.append("NA")
+                        else:
+                            mean, mn, mx = stat(a)
+                            cells.append(f"{ftext(mean)} ({ftext(mn)}-{ftext(mx)})")
+                    f.write(("?" if idx is None else idx, *cells))
+
+
+def versus_reference(data, reference, work: Path, align=True, metric=None, extra=None, fmt="{:.4f}", missing="NA", multiply=False):
+    metric = metric or DistanceMetric.Uncorrected()
+    extra = extra if extra is not None else [DistanceMetric.UncorrectedWithGaps(), DistanceMetric.JukesCantor(), DistanceMetric.Kimura2P()]
+    extra = [m for m in extra if m != metric]
+    work = Path(work)
+    (work / "distances").mkdir(parents=True, exist_ok=True)
+    data = [s.normalize() for s in data] if align else list(data)
+    reference = [s.normalize() for s in reference] if align else list(reference)
+
+    def distances():
+        with SequencePairHandler.Formatted(work / "aligned_pairs.txt", "w") as pairs_file, \
+                DistanceHandler.Linear.WithExtras(work / "distances" / f"{metric}.linear.tsv", "w", missing=missing, formatter=fmt) as linear, \
+                DistanceHandler.Matrix(work / "distances" / f"{metric}.matricial.tsv", "w", missing=missing, formatter=fmt) as matrix:
+            for x in data:
+                for y in reference:
+                    pair = SequencePair(x, y)
+                    if align:
+                        pair = oracle_align(pair)
+                        pairs_file.write(pair)
+                    d = oracle_metric(metric, pair.x, pair.y)
+                    if d is not None and multiply:
+                        d *= 100
+                    dist = Distance(metric, pair.x, pair.y, d)
+                    linear.write(dist)
+                    matrix.write(dist)
+                    yield dist
+
+    with DistanceHandler.Linear.WithExtras(work / "closest.tsv", "w", missing=missing, formatter=fmt) as closest:
+        for _, group in groupby(distances(), lambda d: d.x.id):
+            best = min((d for d in group if d.d is not None), key=lambda d: d.d)
+            closest.write(best)
+            for m in extra:
+                d = oracle_metric(m, best.x, best.y)
+                if d is not None and multiply:
+                    d *= 100
+                closest.write(Distance(m, best.x, best.y, d))
+    if not align:
+        (work / "aligned_pairs.txt").unlink()
