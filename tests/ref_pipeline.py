@@ -172,3 +172,142 @@ def versus_reference(data, reference, work: Path, align=True, metric=None, extra
                 closest.write(Distance(m, best.x, best.y, d))
     if not align:
         (work / "aligned_pairs.txt").unlink()
+
+
+# ---- dereplicate / decontaminate (dereplicate.py:393-440, decontaminate.py:336-371, decontaminate2.py) ----
+from taxi2_b200.sequences import SequenceHandler  # noqa: E402
+
+
+def _out_handler(path: Path, fasta: bool):
+    if fasta:
+        return SequenceHandler.Fasta(path, "w", write_organism=True)
+    return SequenceHandler.Tabfile(path, "w", idHeader="seqid", seqHeader="sequence")
+
+
+def dereplicate(sequences, work: Path, similarity=0.07, length=10, align=True, metric=None, fmt="{:.4f}", missing="NA",
+                multiply=False, fasta=False):
+    metric = metric or DistanceMetric.Uncorrected()
+    work = Path(work)
+    (work / "distances").mkdir(parents=True, exist_ok=True)
+    ext = ".fas" if fasta else ".tsv"
+    data = [s for s in sequences if len(s.seq) >= length]
+    excluded = set()
+    text = lambda v: missing if v is None else fmt.format(v)  # noqa: E731
+
+    def infos(pairs_file, linear, matrix):
+        for x in data:
+            for y in data:
+                if x.id == y.id:
+                    continue
+                if x.id in excluded or y.id in excluded:
+                    continue
+                pair = SequencePair(x, y)
+                if align:
+                    pair = oracle_align(SequencePair(x.normalize(), y.normalize()))
+                    pairs_file.write(pair)
+                d = oracle_metric(metric, pair.x, pair.y)
+                if d is not None and multiply:
+                    d *= 100
+                dist = Distance(metric, pair.x, pair.y, d)
+                linear.write(dist)
+                matrix.write(dist)
+                yield (x.id, y.id, len(x.seq), len(y.seq), d, False if d is None else bool(d <= similarity))
+
+    with SequencePairHandler.Formatted(work / "aligned_pairs.txt", "w") as pairs_file, \
+            DistanceHandler.Linear.WithExtras(work / "distances" / f"{metric}.linear.tsv", "w", missing=missing, formatter=fmt) as linear, \
+            DistanceHandler.Matrix(work / "distances" / f"{metric}.matricial.tsv", "w", missing=missing, formatter=fmt) as matrix, \
+            FileHandler.Tabfile(work / "summary.tsv", "w", columns=("query_id", "query_length", "included_id", "included_length",
+                                                                    "included_distance", "excluded_id", "excluded_length",
+                                                                    "excluded_distance")) as summary:
+        for _, group in groupby(infos(pairs_file, linear, matrix), lambda t: t[0]):
+            first = next(group)
+            query_id, query_length = first[0], first[2]
+            max_id, max_length, max_distance = first[0], first[2], first[4]
+            from itertools import chain
+            for _, id_y, _, len_y, distance, similar in chain([first], group):
+                if not similar:
+                    continue
+                if len_y > max_length:
+                    inc, exc = (id_y, len_y, distance), (max_id, max_length, max_distance)
+                else:
+                    inc, exc = (max_id, max_length, max_distance), (id_y, len_y, distance)
+                excluded.add(exc[0])
+                summary.write((query_id, str(query_length), inc[0], str(inc[1]), text(inc[2]), exc[0], str(exc[1]), text(exc[2])))
+                if len_y > max_length:
+                    max_id, max_length, max_distance = id_y, len_y, distance
+    if not align:
+        (work / "aligned_pairs.txt").unlink()
+    with _out_handler(work / f"dereplicated{ext}", fasta) as kept, _out_handler(work / f"excluded{ext}", fasta) as dropped:
+        for s in data:
+            (dropped if s.id in excluded else kept).write(s)
+    return excluded
+
+
+def _group_minimums(data, group, align, metric, multiply, pairs_path, linear_path, matrix_path, fmt, missing):
+    xs = [s.normalize() for s in data] if align else list(data)
+    ys = [s.normalize() for s in group] if align else list(group)
+    pairs_path.parent.mkdir(parents=True, exist_ok=True)
+    linear_path.parent.mkdir(parents=True, exist_ok=True)
+
+    def distances():
+        with SequencePairHandler.Formatted(pairs_path, "w") as pairs_file, \
+                DistanceHandler.Linear.WithExtras(linear_path, "w", missing=missing, formatter=fmt) as linear, \
+                DistanceHandler.Matrix(matrix_path, "w", missing=missing, formatter=fmt) as matrix:
+            for x in xs:
+                for y in ys:
+                    pair = SequencePair(x, y)
+                    if align:
+                        pair = oracle_align(pair)
+                        pairs_file.write(pair)
+                    d = oracle_metric(metric, pair.x, pair.y)
+                    if d is not None and multiply:
+                        d *= 100
+                    dist = Distance(metric, pair.x, pair.y, d)
+                    linear.write(dist)
+                    matrix.write(dist)
+                    yield dist
+
+    out = [min(grp, key=lambda d: d.d if d.d is not None else inf) for _, grp in groupby(distances(), lambda d: d.x.id)]
+    if not align:
+        pairs_path.unlink()
+    return out
+
+
+def decontaminate(data, outgroup, work: Path, similarity=0.07, align=True, metric=None, fmt="{:.4f}", missing="NA",
+                  multiply=False, fasta=False):
+    metric = metric or DistanceMetric.Uncorrected()
+    work = Path(work)
+    ext = ".fas" if fasta else ".tsv"
+    text = lambda v: missing if v is None else fmt.format(v)  # noqa: E731
+    mins = _group_minimums(data, outgroup, align, metric, multiply, work / "aligned_pairs.txt",
+                           work / "distances" / f"{metric}.linear.tsv", work / "distances" / f"{metric}.matricial.tsv", fmt, missing)
+    with FileHandler.Tabfile(work / "summary.tsv", "w", columns=("query_id", "outgroup_id", "outgroup_distance", "contaminant")) as summary, \
+            _out_handler(work / f"decontaminated{ext}", fasta) as clean, _out_handler(work / f"contaminants{ext}", fasta) as dirty:
+        for s, best in zip(data, mins):
+            bad = False if best.d is None else bool(best.d <= similarity)
+            (dirty if bad else clean).write(s)
+            summary.write((s.id, best.y.id, text(best.d), "Yes" if bad else "No"))
+
+
+def decontaminate2(data, outgroup, ingroup, work: Path, w_out=1.0, w_in=1.0, align=True, metric=None, fmt="{:.4f}", missing="NA",
+                   multiply=False, fasta=False):
+    metric = metric or DistanceMetric.Uncorrected()
+    work = Path(work)
+    ext = ".fas" if fasta else ".tsv"
+    text = lambda v: missing if v is None else fmt.format(v)  # noqa: E731
+    (work / "aligned_pairs").mkdir(parents=True, exist_ok=True)
+    outs = _group_minimums(data, outgroup, align, metric, multiply, work / "aligned_pairs" / "outgroup.txt",
+                           work / "distances" / f"outgroup.{metric}.linear.tsv", work / "distances" / f"outgroup.{metric}.matricial.tsv", fmt, missing)
+    ins = _group_minimums(data, ingroup, align, metric, False, work / "aligned_pairs" / "ingroup.txt",
+                          work / "distances" / f"ingroup.{metric}.linear.tsv", work / "distances" / f"ingroup.{metric}.matricial.tsv", fmt, missing)
+    if not align:
+        (work / "aligned_pairs").rmdir()
+    with FileHandler.Tabfile(work / "summary.tsv", "w", columns=("query_id", "outgroup_id", "outgroup_distance", "ingroup_id",
+                                                                 "ingroup_distance", "contaminant")) as summary, \
+            _out_handler(work / f"decontaminated{ext}", fasta) as clean, _out_handler(work / f"contaminants{ext}", fasta) as dirty:
+        for s, bo, bi in zip(data, outs, ins):
+            do = None if bo.d is None else bo.d * w_out
+            di = None if bi.d is None else bi.d * w_in
+            bad = False if do is None else (True if di is None else bool(do < di))
+            (dirty if bad else clean).write(s)
+            summary.write((s.id, bo.y.id, text(do), bi.y.id, text(di), "Yes" if bad else "No"))

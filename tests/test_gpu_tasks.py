@@ -98,3 +98,77 @@ def test_versus_reference_raises_without_any_defined_distance(tmp_path):
     task.input.reference = Sequences([Sequence("r", "ACGT")])
     with pytest.raises(ValueError):
         task.start()
+
+
+# ---- dereplicate / decontaminate -------------------------------------------------------------------
+from taxi2_b200.files import FileFormat  # noqa: E402
+from taxi2_b200.tasks import Decontaminate, Decontaminate2, Dereplicate  # noqa: E402
+
+
+def near_duplicates():
+    """The 50-sample plus truncated / mutated copies so that the greedy walk excludes things
+    in the middle of rows (the order-observable part of the reference)."""
+    seqs, _, _ = load("Taxi2test1_50.tab")
+    records = list(seqs)[:24]
+    extra = []
+    for k, s in enumerate(records[:10]):
+        cut = s.seq[: len(s.seq) - 7 * (k + 1)]
+        extra.append(Sequence(f"short{k}", cut, s.extras))
+        extra.append(Sequence(f"long{k}", s.seq + "acgtacgt"[: k + 1], s.extras))
+    records[5:5] = extra[:8]
+    records += extra[8:]
+    records.append(Sequence("tiny", "acgt", {"specimen_voucher": "v", "organism": "o"}))
+    return records
+
+
+@pytest.mark.parametrize("align,write,multiply,fasta", [(True, True, False, False), (True, False, True, True), (False, False, False, False)])
+def test_dereplicate_outputs(tmp_path, align, write, multiply, fasta):
+    records = near_duplicates()
+    task = Dereplicate()
+    task.work_dir = tmp_path / "got"
+    task.progress_handler = SILENT
+    task.input = Sequences(records)
+    task.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
+    task.rows_per_block = 7   # several device blocks: exclusions made in one block shrink the next
+    task.params.pairs.align, task.params.pairs.write = align, write
+    task.params.format.percentage_multiply = multiply
+    task.params.thresholds.similarity = 7.0 if multiply else 0.07
+    task.start()
+    excluded = ref_pipeline.dereplicate(records, tmp_path / "want", similarity=task.params.thresholds.similarity, align=align,
+                                        multiply=multiply, fasta=fasta)
+    if align and not write:
+        (tmp_path / "want" / "aligned_pairs.txt").unlink()
+    assert task.excluded == excluded and len(excluded) >= 10
+    assert_same_tree(task.work_dir, tmp_path / "want")
+
+
+@pytest.mark.parametrize("align,multiply,fasta", [(True, False, False), (True, True, True), (False, False, False)])
+def test_decontaminate_outputs(tmp_path, align, multiply, fasta):
+    seqs, _, _ = load("Taxi2test1_50.tab")
+    records = list(seqs)
+    data, outgroup, ingroup = records[:14], records[14:30], records[30:46]
+    data.append(Sequence("allN", "nnnnnnnn", records[0].extras))
+    task = Decontaminate()
+    task.work_dir = tmp_path / "got1"
+    task.progress_handler = SILENT
+    task.input, task.outgroup = Sequences(data), Sequences(outgroup)
+    task.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
+    task.params.pairs.align = align
+    task.params.format.percentage_multiply = multiply
+    task.params.thresholds.similarity = 12.0 if multiply else 0.12
+    task.start()
+    ref_pipeline.decontaminate(data, outgroup, tmp_path / "want1", similarity=task.params.thresholds.similarity, align=align,
+                               multiply=multiply, fasta=fasta)
+    assert_same_tree(task.work_dir, tmp_path / "want1")
+
+    task2 = Decontaminate2()
+    task2.work_dir = tmp_path / "got2"
+    task2.progress_handler = SILENT
+    task2.input, task2.outgroup, task2.ingroup = Sequences(data), Sequences(outgroup), Sequences(ingroup)
+    task2.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
+    task2.params.pairs.align = align
+    task2.params.format.percentage_multiply = multiply
+    task2.params.weights.outgroup, task2.params.weights.ingroup = 1.0, 1.5
+    task2.start()
+    ref_pipeline.decontaminate2(data, outgroup, ingroup, tmp_path / "want2", w_out=1.0, w_in=1.5, align=align, multiply=multiply, fasta=fasta)
+    assert_same_tree(task2.work_dir, tmp_path / "want2")
