@@ -53,6 +53,14 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
     return r;
 }
 
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel)
+{
+    // PRMT without the "selector & 0x7777" that __byte_perm adds (our selector nibbles are 0..7)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
 template <int H> struct Pair16Geom {
     static constexpr int WORDS = (H + 1) / 2;                 // trace words per (lane, step): 2 rows x 2 pairs each
     static constexpr int HB = (WORDS * 4 + 15) / 16 * 16;     // bytes per (lane, step)
@@ -62,7 +70,7 @@ template <int H> struct Pair16Geom {
 template <int H>
 __device__ __forceinline__ void traceback16(const AlignArgs& a, long long p, int lane, const uint8_t* trace, int half,
                                             const uint8_t* __restrict__ x, const uint8_t* __restrict__ y,
-                                            int nA, int nB, int state, int score)
+                                            int nA, int nB, int state, int score, int off = 0, int l0 = 0)
 {
     constexpr int HB = Pair16Geom<H>::HB;
     int i = nA, j = nB;
@@ -76,8 +84,9 @@ __device__ __forceinline__ void traceback16(const AlignArgs& a, long long p, int
         const bool valid = ii >= 1 && jj >= 1;
         int tb = 0, ca = 0, cb = 0;
         if (valid) {
-            const int l = (ii - 1) / H, r = (ii - 1) % H;
-            tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l) * 32 + l) * HB + 2 * r + half);
+            const int slot = off + ii - 1;   // row -> register slot (top-aligned: off = 0)
+            const int l = slot / H, r = slot % H;
+            tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + half);
             ca = (int)__ldg(x + ii - 1);
             cb = (int)__ldg(y + jj - 1);
         }
@@ -231,7 +240,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     const uint32_t sel = lop3_xor_or(a2[r], b2, 0x7070u);
-                    const uint32_t sub = __byte_perm((uint32_t)f.D16, 0u, sel);   // (D16 or 0) per half
+                    const uint32_t sub = prmt_raw((uint32_t)f.D16, 0u, sel);   // (D16 or 0) per half
                     const uint32_t Mr = Hd + sub;
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);                   // 4-bit trace code per half (+ score bits above)
@@ -280,9 +289,140 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     }
 }
 
+__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b)
+{
+    // a + b issued as IMAD (fma pipe): the alu pipe is the bottleneck of this kernel
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+// Bottom-aligned variant: the rows of each pair are shifted (per half) so that row nA always sits
+// in the last register slot of lane 31.  The only rows with special (end-gap) constants are then
+// row nA -- a fixed slot -- and the border row 0, which is kept as an ordinary row whose Iy chain
+// reproduces the leading end gap by itself (requires internal extend == end extend, checked on
+// the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
+// infinity".
+template <int H>
+__device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
+{
+    constexpr int HB = Pair16Geom<H>::HB;
+    constexpr int WORDS = Pair16Geom<H>::WORDS;
+    constexpr int SL = 32 * H;
+    const Fast16& f = a.f16;
+    const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
+    const int offA = SL - A.nA, offB = SL - B.nA;        // slot of row 1; row 0 sits in slot off-1
+    const int l0 = (min(offA, offB) - 1) / H;            // first lane that holds a row >= 0
+    const int nBmax = max(A.nB, B.nB);
+    const int nsteps = nBmax + (31 - l0);
+    const bool live = lane >= l0;
+    const uint32_t NEG2 = pack16(F16_NEG, F16_NEG);
+
+    auto col0_H = [&](int i) -> uint32_t {   // H(i, 0): Ix border for i >= 1, M(0,0) for i == 0, dead above
+        if (i >= 1) return F16_BIAS - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;
+        return i == 0 ? F16_BIAS + 3u : F16_NEG;
+    };
+
+    uint32_t a2[H], Hl[H], Yn[H];
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+        const int s = lane * H + r;
+        const int iA = s - offA + 1, iB = s - offB + 1;
+        const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
+        const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
+        a2[r] = c0 | (c1 << 8);
+        Hl[r] = pack16(col0_H(iA), col0_H(iB));
+        // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
+        const uint32_t y0 = F16_BIAS - f.PeoY + 8u;
+        Yn[r] = pack16(iA == 0 ? y0 : F16_NEG, iB == 0 ? y0 : F16_NEG);
+    }
+    const int itA = lane * H - offA, itB = lane * H - offB;   // row above my top slot
+    uint32_t Hd_saved = pack16(col0_H(itA), col0_H(itB));
+    // Iy constants: internal everywhere except the very last slot (row nA of both pairs)
+    const uint32_t ncYMi = pack16((uint32_t)(5 - f.PoY), (uint32_t)(5 - f.PoY));
+    const uint32_t cYYi = pack16((uint32_t)(f.PeY + 1), (uint32_t)(f.PeY + 1));
+    const uint32_t ncYMl = (lane == 31) ? pack16((uint32_t)(5 - f.PeoY), (uint32_t)(5 - f.PeoY)) : ncYMi;
+    const uint32_t cYYl = (lane == 31) ? pack16((uint32_t)(f.PeeY + 1), (uint32_t)(f.PeeY + 1)) : cYYi;
+    const uint32_t ncXMi = pack16((uint32_t)(1 - f.PoX), (uint32_t)(1 - f.PoX));
+    const uint32_t cXXi = pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
+
+    uint32_t outX = NEG2, outH = NEG2, finA = 0, finB = 0;
+    uint8_t* tbase = trace + (size_t)lane * HB;
+    const int tA = A.nB - 1 + (31 - l0), tB = B.nB - 1 + (31 - l0);   // steps at which lane 31 finishes column nB
+    int t = 0;
+#pragma unroll 1
+    for (int seg = 0; seg < 3; ++seg) {
+        const int tend = (seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps);
+        for (; t < tend; ++t) {
+            const int j = t - (lane - l0) + 1;
+            uint32_t rX = __shfl_up_sync(TAXI_FULL_MASK, outX, 1);
+            uint32_t rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
+            if (lane == 0) { rX = NEG2; rH = NEG2; }   // nothing above slot 0
+            const bool active = live && j >= 1 && j <= nBmax;
+            if (active) {
+                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : 7u;
+                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : 7u;
+                const uint32_t b2 = b0 | (b1 << 8);
+                uint32_t ncXM = ncXMi, cXX = cXXi;
+                if (j == A.nB || j == B.nB) {   // a vertical gap in a pair's last column is an end gap
+                    const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
+                    const int xe0 = (j == A.nB) ? f.PeeX : f.PeX, xe1 = (j == B.nB) ? f.PeeX : f.PeX;
+                    ncXM = pack16((uint32_t)(1 - xo0), (uint32_t)(1 - xo1));
+                    cXX = pack16((uint32_t)(xe0 + 2), (uint32_t)(xe1 + 2));
+                }
+                uint32_t Xin = rX;
+                uint32_t tw[WORDS];
+                uint32_t tprev = 0;
+                uint32_t Mr = add_fma_pipe(Hd_saved, prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[0], b2, 0x7070u)));
+#pragma unroll
+                for (int r = 0; r < H; ++r) {
+                    uint32_t Mr_next = 0;
+                    if (r + 1 < H)   // diagonal term of the next row needs H(i, j-1) before it is overwritten
+                        Mr_next = add_fma_pipe(Hl[r], prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r + 1], b2, 0x7070u)));
+                    const uint32_t Yin = Yn[r];
+                    const uint32_t tc = lop3_or3(Mr, Xin, Yin);
+                    const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
+                    const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
+                    const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
+                    Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
+                    Xin = __viaddmax_u16x2(Mt, ncXM, Xt - cXX);
+                    Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt - ((r == H - 1) ? cYYl : cYYi));
+                    if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
+                    else if (r == H - 1) tw[r >> 1] = __byte_perm(tc, 0u, 0x6420);
+                    tprev = tc;
+                    Mr = Mr_next;
+                }
+                outX = Xin;
+                outH = Hl[H - 1];
+                Hd_saved = rH;
+                uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+#pragma unroll
+                for (int k = 0; k < HB / 16; ++k) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[q] = (4 * k + q < WORDS) ? tw[4 * k + q] : 0u;
+                    __stcg(dst + k, make_uint4(w[0], w[1], w[2], w[3]));
+                }
+            }
+        }
+        if (t - 1 == tA) finA = Hl[H - 1] & 0xFFFFu;
+        if (t - 1 == tB) finB = Hl[H - 1] >> 16;
+    }
+    finA = __shfl_sync(TAXI_FULL_MASK, finA, 31);
+    finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
+    __syncwarp();
+
+    const int scoreA = ((int)(finA & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * A.nA;
+    traceback16<H>(a, p0, lane, trace, 0, A.xb, A.yb, A.nA, A.nB, 3 - (int)(finA & 3u), scoreA, offA, l0);
+    if (p1 != p0) {
+        const int scoreB = ((int)(finB & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * B.nA;
+        traceback16<H>(a, p1, lane, trace, 1, B.xb, B.yb, B.nA, B.nB, 3 - (int)(finB & 3u), scoreB, offB, l0);
+    }
+}
+
 constexpr int PAIR16_WARPS_PER_BLOCK = 4;
 
-template <int H>
+template <int H, bool BOTTOM>
 __global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32)
 gotoh_pair16_kernel(const AlignArgs a)
 {
@@ -297,7 +437,8 @@ gotoh_pair16_kernel(const AlignArgs a)
         if (u >= units) break;
         const long long p0 = (long long)(2ULL * u);
         const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
-        align_two<H>(a, p0, p1, lane, trace);
+        if constexpr (BOTTOM) align_two_bottom<H>(a, p0, p1, lane, trace);
+        else align_two<H>(a, p0, p1, lane, trace);
         __syncwarp();
     }
 }

@@ -85,6 +85,7 @@ struct taxi_ctx {
     bool codebook_ok = true;
     DevBuf<uint8_t> d_codebook;
     int force_general = 0;          // option: always use the general int32 kernel
+    int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
     DevBuf<uint8_t> trace;
@@ -166,24 +167,24 @@ __global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, int64_t n
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = lut[bytes[k]];
 }
 
-template <int H> cudaError_t occupancy16(int* blocks_per_sm)
+template <int H, bool BOTTOM> cudaError_t occupancy16(int* blocks_per_sm)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H>, PAIR16_WARPS_PER_BLOCK * 32, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H, BOTTOM>, PAIR16_WARPS_PER_BLOCK * 32, 0);
 }
 
-template <int H> void launch_pair16(const AlignArgs& a, int grid, cudaStream_t st)
+template <int H, bool BOTTOM> void launch_pair16(const AlignArgs& a, int grid, cudaStream_t st)
 {
-    gotoh_pair16_kernel<H><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
+    gotoh_pair16_kernel<H, BOTTOM><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
 }
 
-const Dispatch kDispatch16[] = {
-    {8, occupancy16<8>, launch_pair16<8>, Pair16Geom<8>::HB},     {12, occupancy16<12>, launch_pair16<12>, Pair16Geom<12>::HB},
-    {16, occupancy16<16>, launch_pair16<16>, Pair16Geom<16>::HB}, {21, occupancy16<21>, launch_pair16<21>, Pair16Geom<21>::HB},
-    {24, occupancy16<24>, launch_pair16<24>, Pair16Geom<24>::HB}, {32, occupancy16<32>, launch_pair16<32>, Pair16Geom<32>::HB},
-};
+#define P16(H, B) {H, occupancy16<H, B>, launch_pair16<H, B>, Pair16Geom<H>::HB}
+const Dispatch kDispatch16[] = {P16(8, false), P16(12, false), P16(16, false), P16(21, false), P16(24, false), P16(32, false)};
+// bottom-aligned rows (needs internal extend == end extend and one spare row slot)
+const Dispatch kDispatch16b[] = {P16(8, true), P16(12, true), P16(16, true), P16(21, true), P16(24, true), P16(32, true)};
+#undef P16
 
 // Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
-bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out, int* H_out)
+bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out, int* H_out, bool* bottom_out)
 {
     if (c->force_general || !c->codebook_ok) return false;
     const int32_t* s = c->raw_scores;
@@ -207,9 +208,10 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
             if (O[ty] + E[tx] - beta >= 0) return false;     // b > a
             if (O[tx] + O[ty] - beta >= 0) return false;     // a == b
         }
-    // geometry: single stripe
+    // geometry: single stripe; the bottom-aligned variant keeps the border row in a slot of its own
+    const bool bottom = (ie == ee) && !c->force_top;
     int H = 0;
-    for (const auto& e : kDispatch16) if (32 * e.H >= max_rows) { H = e.H; break; }
+    for (const auto& e : kDispatch16) if (32 * e.H >= max_rows + (bottom ? 1 : 0)) { H = e.H; break; }
     if (!H) return false;
     Fast16 f;
     f.D16 = 16 * D; f.beta = beta;
@@ -219,10 +221,10 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     const long long R = 32LL * H, C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
     const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
-    if (pen_o > 2000 || pen_e > 2000) return false;
+    if (pen_o > 1500 || pen_e > 1500) return false;   // dead slots idle at F16_NEG - one penalty: must stay >= 0
     const long long lower = 2 * pen_o + (R + C) * pen_e, upper = (long long)f.D16 * std::min(R, C);
     if (0x8000LL - lower < 0x0800LL + 2 * 2048 || 0x8000LL + upper > 65000) return false;
-    *out = f; *H_out = H;
+    *out = f; *H_out = H; *bottom_out = bottom;
     return true;
 }
 
@@ -232,10 +234,11 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
 {
     Fast16 f16{};
     int H = 0;
-    const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H);
+    bool bottom = false;
+    const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H, &bottom);
     if (!fast) H = pick_H(max_rows);
     const Dispatch* d = nullptr;
-    if (fast) { for (const auto& e : kDispatch16) if (e.H == H) d = &e; }
+    if (fast) { for (const auto& e : (bottom ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
     else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
     int bps = 0;
     CUDA_TRY(d->occ(&bps));
@@ -245,7 +248,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     const long long per_warp = ((nstripes * (max_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (max_cols + 2);
     const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;
-    c->last_kernel = fast ? 16 : 32;
+    c->last_kernel = fast ? (bottom ? 17 : 16) : 32;
     a.f16 = f16;
     // resident warps, capped by pairs and by a trace-arena budget of half the free memory
     size_t free_b = 0, total_b = 0;
@@ -744,6 +747,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
 {
     if (!c || !key) return fail(TAXI_E_ARG, "null argument");
     if (std::strcmp(key, "force_general") == 0) { c->force_general = value; return TAXI_OK; }
+    if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }
 

@@ -50,8 +50,9 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
     px = np.arange(n, dtype=np.int32)
     want = oracle_batch(xs, ys, px, px, scores)
     kernels = set()
-    for force_general in (0, 1):
+    for force_general, force_top in ((0, 0), (0, 1), (1, 0)):
         engine.set_option("force_general", force_general)
+        engine.set_option("force_top", force_top)
         try:
             engine.set_scores(scores)
             engine.load(xs, 0)
@@ -71,6 +72,7 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
                     assert ax[k].decode("latin-1") == ox and ay[k].decode("latin-1") == oy, (force_general, k, xs[k], ys[k])
         finally:
             engine.set_option("force_general", 0)
+            engine.set_option("force_top", 0)
     if expect_fast is True:
         assert 16 in kernels, "packed fast path was expected to be eligible"
     if expect_fast is False:
@@ -124,7 +126,7 @@ def test_fast_path_score_sets(engine):
     rng = np.random.default_rng(16)
     xs, ys = random_pairs(rng, 300, 1, 120, sub=0.2, indel=0.06, alphabet=b"ACGTN")
     xs2, ys2 = random_pairs(rng, 300, 1, 120, sub=0.3, indel=0.1, alphabet=b"AT")
-    for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (5, -4, -10, -4, -4, -4), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2)]:
+    for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (5, -4, -10, -4, -4, -4), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2), (2, -2, -7, -3, -4, -2)]:
         check_pairs(engine, xs, ys, scores, expect_fast=True)
         check_pairs(engine, xs2, ys2, scores, expect_fast=True)
 
