@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libtaxi2_b200.so"
+# TAXI2_B200_LIB points at an alternative build of the same library (kernel experiments)
+LIB_PATH = Path(os.environ.get("TAXI2_B200_LIB") or (_PKG / "lib" / "libtaxi2_b200.so"))
 
 OUT_SCORE, OUT_COUNTS, OUT_METRICS = 1, 2, 4
 

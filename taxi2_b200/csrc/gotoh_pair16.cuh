@@ -289,12 +289,22 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     }
 }
 
-__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b)
+#ifndef PAIR16_FMA_ADDS
+#define PAIR16_FMA_ADDS 0
+#endif
+
+__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b, uint32_t one)
 {
-    // a + b issued as IMAD (fma pipe): the alu pipe is the bottleneck of this kernel
+    // a + b issued as IMAD a*one+b (fma pipe; `one` is a kernel parameter equal to 1, so ptxas
+    // cannot fold it back into an ALU add): the alu pipe is the bottleneck of this kernel
+#if PAIR16_FMA_ADDS
     uint32_t r;
-    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
     return r;
+#else
+    (void)one;
+    return a + b;
+#endif
 }
 
 // Bottom-aligned variant: the rows of each pair are shifted (per half) so that row nA always sits
@@ -303,8 +313,17 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b)
 // reproduces the leading end gap by itself (requires internal extend == end extend, checked on
 // the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
 // infinity".
-template <int H>
-__device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
+// With LUT = true the substitution increments come from a per-warp shared-memory table
+// lut[half][symbol b][row slot][lane] (u16: 16*(match-beta) where the row's symbol equals b, else
+// 0) instead of the LOP3 + PRMT pair: two LDS.U16 (load/store pipe, otherwise idle) and one IMAD
+// replace two alu-pipe instructions per row, which is the pipe this kernel saturates.  Needs the
+// plain 5-symbol alphabet (A C G T N; symbol 5 = padding past the end of y).
+constexpr int LUT_SYMBOLS = 6;
+template <int H> struct Pair16Lut { static constexpr int BYTES = 2 * LUT_SYMBOLS * H * 32 * 2; };
+
+template <int H, bool LUT>
+__device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace,
+                                                 uint16_t* lut)
 {
     constexpr int HB = Pair16Geom<H>::HB;
     constexpr int WORDS = Pair16Geom<H>::WORDS;
@@ -331,6 +350,13 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
         const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
         const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
         a2[r] = c0 | (c1 << 8);
+        if constexpr (LUT) {
+#pragma unroll
+            for (int c = 0; c < LUT_SYMBOLS; ++c) {
+                lut[((0 * LUT_SYMBOLS + c) * H + r) * 32 + lane] = (uint16_t)((c0 == (uint32_t)c) ? f.D16 : 0);
+                lut[((1 * LUT_SYMBOLS + c) * H + r) * 32 + lane] = (uint16_t)((c1 == (uint32_t)c) ? f.D16 : 0);
+            }
+        }
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
         // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
         const uint32_t y0 = F16_BIAS - f.PeoY + 8u;
@@ -340,12 +366,17 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     uint32_t Hd_saved = pack16(col0_H(itA), col0_H(itB));
     // Iy constants: internal everywhere except the very last slot (row nA of both pairs)
     const uint32_t ncYMi = pack16((uint32_t)(5 - f.PoY), (uint32_t)(5 - f.PoY));
-    const uint32_t cYYi = pack16((uint32_t)(f.PeY + 1), (uint32_t)(f.PeY + 1));
+    // the "subtract a packed non-negative constant" steps are done as x + (-c) with a full 32-bit
+    // negation of the packed constant (no borrow can cross the halves, see the header comment)
+    const uint32_t one = f.one;
+    const uint32_t cYYi = 0u - pack16((uint32_t)(f.PeY + 1), (uint32_t)(f.PeY + 1));
     const uint32_t ncYMl = (lane == 31) ? pack16((uint32_t)(5 - f.PeoY), (uint32_t)(5 - f.PeoY)) : ncYMi;
-    const uint32_t cYYl = (lane == 31) ? pack16((uint32_t)(f.PeeY + 1), (uint32_t)(f.PeeY + 1)) : cYYi;
+    const uint32_t cYYl = (lane == 31) ? 0u - pack16((uint32_t)(f.PeeY + 1), (uint32_t)(f.PeeY + 1)) : cYYi;
     const uint32_t ncXMi = pack16((uint32_t)(1 - f.PoX), (uint32_t)(1 - f.PoX));
-    const uint32_t cXXi = pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
+    const uint32_t cXXi = 0u - pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
 
+    if constexpr (LUT) __syncwarp();
+    constexpr uint32_t PAD = LUT ? 5u : 7u;   // symbol past the end of y: matches nothing
     uint32_t outX = NEG2, outH = NEG2, finA = 0, finB = 0;
     uint8_t* tbase = trace + (size_t)lane * HB;
     const int tA = A.nB - 1 + (31 - l0), tB = B.nB - 1 + (31 - l0);   // steps at which lane 31 finishes column nB
@@ -360,33 +391,39 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
             if (lane == 0) { rX = NEG2; rH = NEG2; }   // nothing above slot 0
             const bool active = live && j >= 1 && j <= nBmax;
             if (active) {
-                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : 7u;
-                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : 7u;
+                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
+                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
                 const uint32_t b2 = b0 | (b1 << 8);
+                const uint16_t* lutA = lut + (b0 * H) * 32 + lane;
+                const uint16_t* lutB = lut + ((LUT_SYMBOLS + b1) * H) * 32 + lane;
+                auto sub_of = [&](int r) -> uint32_t {
+                    if constexpr (LUT) return (uint32_t)lutB[r * 32] * 65536u + (uint32_t)lutA[r * 32];
+                    else return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u));
+                };
                 uint32_t ncXM = ncXMi, cXX = cXXi;
                 if (j == A.nB || j == B.nB) {   // a vertical gap in a pair's last column is an end gap
                     const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
                     const int xe0 = (j == A.nB) ? f.PeeX : f.PeX, xe1 = (j == B.nB) ? f.PeeX : f.PeX;
                     ncXM = pack16((uint32_t)(1 - xo0), (uint32_t)(1 - xo1));
-                    cXX = pack16((uint32_t)(xe0 + 2), (uint32_t)(xe1 + 2));
+                    cXX = 0u - pack16((uint32_t)(xe0 + 2), (uint32_t)(xe1 + 2));
                 }
                 uint32_t Xin = rX;
                 uint32_t tw[WORDS];
                 uint32_t tprev = 0;
-                uint32_t Mr = add_fma_pipe(Hd_saved, prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[0], b2, 0x7070u)));
+                uint32_t Mr = add_fma_pipe(sub_of(0), Hd_saved, one);
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     uint32_t Mr_next = 0;
                     if (r + 1 < H)   // diagonal term of the next row needs H(i, j-1) before it is overwritten
-                        Mr_next = add_fma_pipe(Hl[r], prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r + 1], b2, 0x7070u)));
+                        Mr_next = add_fma_pipe(sub_of(r + 1), Hl[r], one);
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
                     const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
                     const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
                     Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
-                    Xin = __viaddmax_u16x2(Mt, ncXM, Xt - cXX);
-                    Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt - ((r == H - 1) ? cYYl : cYYi));
+                    Xin = __viaddmax_u16x2(Mt, ncXM, add_fma_pipe(cXX, Xt, one));
+                    Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, add_fma_pipe((r == H - 1) ? cYYl : cYYi, Yt, one));
                     if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
                     else if (r == H - 1) tw[r >> 1] = __byte_perm(tc, 0u, 0x6420);
                     tprev = tc;
@@ -420,12 +457,28 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     }
 }
 
-constexpr int PAIR16_WARPS_PER_BLOCK = 4;
+#ifndef PAIR16_WPB
+#define PAIR16_WPB 4
+#endif
+constexpr int PAIR16_WARPS_PER_BLOCK = PAIR16_WPB;
 
-template <int H, bool BOTTOM>
-__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32)
+#ifndef PAIR16_MIN_BLOCKS
+#define PAIR16_MIN_BLOCKS 3
+#endif
+
+#ifdef PAIR16_MAXNREG
+#define PAIR16_BOUNDS __maxnreg__(PAIR16_MAXNREG)
+#else
+#define PAIR16_BOUNDS __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, PAIR16_MIN_BLOCKS)
+#endif
+
+// MODE 0: top-aligned rows; 1: bottom-aligned; 2: bottom-aligned + shared-memory substitution table
+template <int H, int MODE>
+__global__ void PAIR16_BOUNDS
 gotoh_pair16_kernel(const AlignArgs a)
 {
+    extern __shared__ __align__(16) uint8_t pair16_smem[];
+    uint16_t* lut = reinterpret_cast<uint16_t*>(pair16_smem + (size_t)(threadIdx.x >> 5) * Pair16Lut<H>::BYTES);
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * PAIR16_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     uint8_t* trace = a.trace + gw * a.trace_per_warp;
@@ -437,7 +490,8 @@ gotoh_pair16_kernel(const AlignArgs a)
         if (u >= units) break;
         const long long p0 = (long long)(2ULL * u);
         const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
-        if constexpr (BOTTOM) align_two_bottom<H>(a, p0, p1, lane, trace);
+        if constexpr (MODE == 2) align_two_bottom<H, true>(a, p0, p1, lane, trace, lut);
+        else if constexpr (MODE == 1) align_two_bottom<H, false>(a, p0, p1, lane, trace, lut);
         else align_two<H>(a, p0, p1, lane, trace);
         __syncwarp();
     }
