@@ -318,8 +318,21 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b, uint32_
 // 0) instead of the LOP3 + PRMT pair: two LDS.U16 (load/store pipe, otherwise idle) and one IMAD
 // replace two alu-pipe instructions per row, which is the pipe this kernel saturates.  Needs the
 // plain 5-symbol alphabet (A C G T N; symbol 5 = padding past the end of y).
+//
+// Layout: every lane keeps its entries in "its own" bank -- u16 entry e = b*HP + r of a half lives
+// in 32-bit word (e/2)*32 + lane, halfword e&1 -- so the LDS.U16 of a warp never conflict, whatever
+// symbols the 32 lanes look up (HP = H rounded up to even keeps the address affine in r).
 constexpr int LUT_SYMBOLS = 6;
-template <int H> struct Pair16Lut { static constexpr int BYTES = 2 * LUT_SYMBOLS * H * 32 * 2; };
+template <int H> struct Pair16Lut {
+    static constexpr int HP = (H + 1) / 2 * 2;
+    static constexpr int HALF_U16 = LUT_SYMBOLS * HP * 32;     // u16 entries per half
+    static constexpr int BYTES = 2 * HALF_U16 * 2;
+    __device__ static __forceinline__ int index(int half, int b, int r, int lane)
+    {
+        const int e = b * HP + r;
+        return half * HALF_U16 + ((e >> 1) * 32 + lane) * 2 + (e & 1);
+    }
+};
 
 template <int H, bool LUT>
 __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace,
@@ -353,8 +366,8 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
         if constexpr (LUT) {
 #pragma unroll
             for (int c = 0; c < LUT_SYMBOLS; ++c) {
-                lut[((0 * LUT_SYMBOLS + c) * H + r) * 32 + lane] = (uint16_t)((c0 == (uint32_t)c) ? f.D16 : 0);
-                lut[((1 * LUT_SYMBOLS + c) * H + r) * 32 + lane] = (uint16_t)((c1 == (uint32_t)c) ? f.D16 : 0);
+                lut[Pair16Lut<H>::index(0, c, r, lane)] = (uint16_t)((c0 == (uint32_t)c) ? f.D16 : 0);
+                lut[Pair16Lut<H>::index(1, c, r, lane)] = (uint16_t)((c1 == (uint32_t)c) ? f.D16 : 0);
             }
         }
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
@@ -394,10 +407,14 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
                 const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
                 const uint32_t b2 = b0 | (b1 << 8);
-                const uint16_t* lutA = lut + (b0 * H) * 32 + lane;
-                const uint16_t* lutB = lut + ((LUT_SYMBOLS + b1) * H) * 32 + lane;
+                const uint16_t* lutA = lut + Pair16Lut<H>::index(0, (int)b0, 0, lane);
+                const uint16_t* lutB = lut + Pair16Lut<H>::index(1, (int)b1, 0, lane);
                 auto sub_of = [&](int r) -> uint32_t {
-                    if constexpr (LUT) return (uint32_t)lutB[r * 32] * 65536u + (uint32_t)lutA[r * 32];
+                    constexpr int dummy = 0; (void)dummy;
+                    if constexpr (LUT) {
+                        const int o = (r >> 1) * 64 + (r & 1);   // u16 offset of row r from row 0 (b*HP is even)
+                        return (uint32_t)lutB[o] * 65536u + (uint32_t)lutA[o];
+                    }
                     else return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u));
                 };
                 uint32_t ncXM = ncXMi, cXX = cXXi;
