@@ -322,6 +322,15 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b, uint32_
 // Layout: every lane keeps its entries in "its own" bank -- u16 entry e = b*HP + r of a half lives
 // in 32-bit word (e/2)*32 + lane, halfword e&1 -- so the LDS.U16 of a warp never conflict, whatever
 // symbols the 32 lanes look up (HP = H rounded up to even keeps the address affine in r).
+__device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr)
+{
+    // explicit 16-bit shared load: the sub-word select is free in the load/store unit, whereas the
+    // compiler would fuse neighbouring entries into one LDS.32 and split them with alu-pipe PRMTs
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    return v;
+}
+
 constexpr int LUT_SYMBOLS = 6;
 template <int H> struct Pair16Lut {
     static constexpr int HP = (H + 1) / 2 * 2;
@@ -407,13 +416,12 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
                 const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
                 const uint32_t b2 = b0 | (b1 << 8);
-                const uint16_t* lutA = lut + Pair16Lut<H>::index(0, (int)b0, 0, lane);
-                const uint16_t* lutB = lut + Pair16Lut<H>::index(1, (int)b1, 0, lane);
+                const uint32_t lutA = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(0, (int)b0, 0, lane)) : 0u;
+                const uint32_t lutB = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(1, (int)b1, 0, lane)) : 0u;
                 auto sub_of = [&](int r) -> uint32_t {
-                    constexpr int dummy = 0; (void)dummy;
                     if constexpr (LUT) {
-                        const int o = (r >> 1) * 64 + (r & 1);   // u16 offset of row r from row 0 (b*HP is even)
-                        return (uint32_t)lutB[o] * 65536u + (uint32_t)lutA[o];
+                        const uint32_t o = ((r >> 1) * 64 + (r & 1)) * 2;   // byte offset of row r from row 0 (b*HP is even)
+                        return lds_u16(lutB + o) * 65536u + lds_u16(lutA + o);
                     }
                     else return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u));
                 };
