@@ -322,12 +322,14 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b, uint32_
 // Layout: every lane keeps its entries in "its own" bank -- u16 entry e = b*HP + r of a half lives
 // in 32-bit word (e/2)*32 + lane, halfword e&1 -- so the LDS.U16 of a warp never conflict, whatever
 // symbols the 32 lanes look up (HP = H rounded up to even keeps the address affine in r).
-__device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr, uint32_t epoch)
 {
     // explicit 16-bit shared load: the sub-word select is free in the load/store unit, whereas the
-    // compiler would fuse neighbouring entries into one LDS.32 and split them with alu-pipe PRMTs
+    // compiler would fuse neighbouring entries into one LDS.32 and split them with alu-pipe PRMTs.
+    // Not volatile, so the scheduler may hoist it ahead of its use; `epoch` (the work-unit index)
+    // is a fake input that makes loads of different units distinct values for the optimiser.
     uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+    asm("ld.shared.u16 %0, [%1]; // %2" : "=r"(v) : "r"(smem_addr), "r"(epoch));
     return v;
 }
 
@@ -398,6 +400,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     const uint32_t cXXi = 0u - pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
 
     if constexpr (LUT) __syncwarp();
+    const uint32_t epoch = (uint32_t)p0;
     constexpr uint32_t PAD = LUT ? 5u : 7u;   // symbol past the end of y: matches nothing
     uint32_t outX = NEG2, outH = NEG2, finA = 0, finB = 0;
     uint8_t* tbase = trace + (size_t)lane * HB;
@@ -421,7 +424,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 auto sub_of = [&](int r) -> uint32_t {
                     if constexpr (LUT) {
                         const uint32_t o = ((r >> 1) * 64 + (r & 1)) * 2;   // byte offset of row r from row 0 (b*HP is even)
-                        return lds_u16(lutB + o) * 65536u + lds_u16(lutA + o);
+                        return lds_u16(lutB + o, epoch) * 65536u + lds_u16(lutA + o, epoch);
                     }
                     else return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u));
                 };
