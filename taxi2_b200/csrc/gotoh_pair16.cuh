@@ -66,87 +66,132 @@ template <int H> struct Pair16Geom {
     static constexpr int HB = (WORDS * 4 + 15) / 16 * 16;     // bytes per (lane, step)
 };
 
-// Warp-parallel first-path traceback over the 4-bit codes of one of the two pairs (half = 0/1).
+// Warp-parallel first-path traceback over the 4-bit codes.  The walk is a chain of dependent
+// loads (each iteration needs the previous one's outcome), so the walks of the two pairs a warp
+// has just aligned are advanced in lockstep: both windows' loads are issued before either is
+// consumed, which halves the exposed memory latency.
+struct Walk {
+    const uint8_t* x; const uint8_t* y;   // ASCII of the two sequences
+    long long p;                          // pair index (outputs)
+    int i, j, state;                      // current cell and state (0 = M, 1 = Ix, 2 = Iy)
+    int half, off;                        // which 16-bit half of the arena; row -> slot offset
+    int same, ts, tv, gapc, pend;
+    bool seen;
+    int64_t wpos;                         // write cursor of the gapped strings
+    int score;
+    int tb, ca, cb; bool valid;           // the window element this lane fetched
+};
+
 template <int H>
-__device__ __forceinline__ void traceback16(const AlignArgs& a, long long p, int lane, const uint8_t* trace, int half,
-                                            const uint8_t* __restrict__ x, const uint8_t* __restrict__ y,
-                                            int nA, int nB, int state, int score, int off = 0, int l0 = 0)
+__device__ __forceinline__ void walk_fetch(Walk& w, int lane, const uint8_t* trace, int l0)
 {
     constexpr int HB = Pair16Geom<H>::HB;
-    int i = nA, j = nB;
-    int same = 0, ts = 0, tv = 0, gapc = 0, pend = 0;
-    bool seen = false;
-    const bool strings = a.aln_x != nullptr;
-    int64_t wpos = strings ? a.aln_off[p + 1] : 0;
-    while (i > 0 && j > 0) {
-        const int di = (state != 2), dj = (state != 1);
-        const int ii = i - lane * di, jj = j - lane * dj;
-        const bool valid = ii >= 1 && jj >= 1;
-        int tb = 0, ca = 0, cb = 0;
-        if (valid) {
-            const int slot = off + ii - 1;   // row -> register slot (top-aligned: off = 0)
-            const int l = slot / H, r = slot % H;
-            tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + half);
-            ca = (int)__ldg(x + ii - 1);
-            cb = (int)__ldg(y + jj - 1);
-        }
-        // state I would hand over to if the path reaches my cell in `state`
-        int ns;
-        if (state == 0) ns = 3 - (tb & 3);            // 3 -> M, 2 -> Ix, 1 -> Iy
-        else if (state == 1) ns = (tb & 4) ? 0 : 1;   // Ix: opened from M, or extended
-        else ns = (tb & 8) ? 0 : 2;                   // Iy
-        const unsigned cont = __ballot_sync(TAXI_FULL_MASK, valid && ns == state);
-        const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, valid);
-        const int f = __ffs(~cont) - 1;
-        int V = (f < 0) ? 32 : f + 1;
-        V = min(V, __popc(vmask));
-        const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
-        const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
-        const int ka = (state == 2) ? 4 : base_class(ca);
-        const int kb = (state == 1) ? 4 : base_class(cb);
-        const bool both = ka < 4 && kb < 4;
-        const int d = ka ^ kb;
-        const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
-        const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
-        const unsigned tsm = __ballot_sync(TAXI_FULL_MASK, both && d == 1) & visited;
-        const unsigned tvm = __ballot_sync(TAXI_FULL_MASK, both && d > 1) & visited;
-        if (bm) {
-            ts += __popc(tsm); tv += __popc(tvm); same += __popc(bm & ~(tsm | tvm));
-            const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
-            const unsigned below = (1u << fb) - 1u;
-            const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
-            if (seen) gapc += pend + __popc(gm & below);
-            gapc += __popc(gm & upto & ~below);
-            pend = __popc(gm & ~upto);
-            seen = true;
-        } else {
-            pend += __popc(gm);
-        }
-        if (strings && lane < V) {
-            a.aln_x[wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
-            a.aln_y[wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
-        }
-        wpos -= V;
-        i -= V * di; j -= V * dj;
-        state = next;
+    const int di = (w.state != 2), dj = (w.state != 1);
+    const int ii = w.i - lane * di, jj = w.j - lane * dj;
+    w.valid = w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1;
+    w.tb = 0; w.ca = 0; w.cb = 0;
+    if (w.valid) {
+        const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
+        const int l = slot / H, r = slot % H;
+        w.tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + w.half);
+        w.ca = (int)__ldg(w.x + ii - 1);
+        w.cb = (int)__ldg(w.y + jj - 1);
     }
-    if (strings) {
-        for (int k = lane; k < i; k += 32) { a.aln_x[wpos - 1 - k] = __ldg(x + i - 1 - k); a.aln_y[wpos - 1 - k] = '-'; }
-        wpos -= i;
-        for (int k = lane; k < j; k += 32) { a.aln_x[wpos - 1 - k] = '-'; a.aln_y[wpos - 1 - k] = __ldg(y + j - 1 - k); }
-        wpos -= j;
-        if (lane == 0) a.aln_start[p] = wpos;
+}
+
+__device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int lane)
+{
+    if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
+    const int state = w.state, tb = w.tb;
+    const int di = (state != 2), dj = (state != 1);
+    // state I would hand over to if the path reaches my cell in `state`
+    int ns;
+    if (state == 0) ns = 3 - (tb & 3);            // 3 -> M, 2 -> Ix, 1 -> Iy
+    else if (state == 1) ns = (tb & 4) ? 0 : 1;   // Ix: opened from M, or extended
+    else ns = (tb & 8) ? 0 : 2;                   // Iy
+    const unsigned cont = __ballot_sync(TAXI_FULL_MASK, w.valid && ns == state);
+    const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, w.valid);
+    const int f = __ffs(~cont) - 1;
+    int V = (f < 0) ? 32 : f + 1;
+    V = min(V, __popc(vmask));
+    const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
+    const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
+    const int ka = (state == 2) ? 4 : base_class(w.ca);
+    const int kb = (state == 1) ? 4 : base_class(w.cb);
+    const bool both = ka < 4 && kb < 4;
+    const int d = ka ^ kb;
+    const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
+    const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
+    const unsigned tsm = __ballot_sync(TAXI_FULL_MASK, both && d == 1) & visited;
+    const unsigned tvm = __ballot_sync(TAXI_FULL_MASK, both && d > 1) & visited;
+    if (bm) {
+        w.ts += __popc(tsm); w.tv += __popc(tvm); w.same += __popc(bm & ~(tsm | tvm));
+        const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
+        const unsigned below = (1u << fb) - 1u;
+        const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
+        if (w.seen) w.gapc += w.pend + __popc(gm & below);
+        w.gapc += __popc(gm & upto & ~below);
+        w.pend = __popc(gm & ~upto);
+        w.seen = true;
+    } else {
+        w.pend += __popc(gm);
+    }
+    if (a.aln_x != nullptr && lane < V) {
+        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)w.ca;
+        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)w.cb;
+    }
+    w.wpos -= V;
+    w.i -= V * di; w.j -= V * dj;
+    w.state = next;
+}
+
+__device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lane)
+{
+    if (a.aln_x != nullptr) {
+        // leading end gap: whatever is left of x (vertical) or y (horizontal)
+        for (int k = lane; k < w.i; k += 32) { a.aln_x[w.wpos - 1 - k] = __ldg(w.x + w.i - 1 - k); a.aln_y[w.wpos - 1 - k] = '-'; }
+        w.wpos -= w.i;
+        for (int k = lane; k < w.j; k += 32) { a.aln_x[w.wpos - 1 - k] = '-'; a.aln_y[w.wpos - 1 - k] = __ldg(w.y + w.j - 1 - k); }
+        w.wpos -= w.j;
+        if (lane == 0) a.aln_start[w.p] = w.wpos;
     }
     if (lane != 0) return;
-    if (a.score) a.score[p] = score;
-    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);
+    if (a.score) a.score[w.p] = w.score;
+    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * w.p) = make_int4(w.same, w.ts, w.tv, w.gapc);
     if (a.metrics) {
         double m[4];
-        metrics_from_counts(same, ts, tv, gapc, m);
-        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
+        metrics_from_counts(w.same, w.ts, w.tv, w.gapc, m);
+        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * w.p);
         dst[0] = make_double2(m[0], m[1]);
         dst[1] = make_double2(m[2], m[3]);
     }
+}
+
+__device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, const uint8_t* x, const uint8_t* y, int nA, int nB,
+                                           int half, int off, uint32_t fin, int beta)
+{
+    Walk w;
+    w.x = x; w.y = y; w.p = p; w.i = nA; w.j = nB; w.state = 3 - (int)(fin & 3u);
+    w.half = half; w.off = off;
+    w.same = w.ts = w.tv = w.gapc = w.pend = 0; w.seen = false;
+    w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
+    w.score = ((int)(fin & 0xFFF0u) - (int)F16_BIAS) / 16 + beta * nA;
+    w.tb = w.ca = w.cb = 0; w.valid = false;
+    return w;
+}
+
+template <int H>
+__device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, const uint8_t* trace, int l0, Walk& wa, Walk& wb, bool second)
+{
+    if (!second) { wb.i = 0; wb.j = 0; }
+    while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
+        walk_fetch<H>(wa, lane, trace, l0);
+        walk_fetch<H>(wb, lane, trace, l0);
+        walk_advance(wa, a, lane);
+        walk_advance(wb, a, lane);
+    }
+    walk_finish(wa, a, lane);
+    if (second) walk_finish(wb, a, lane);
 }
 
 struct PairRef {
@@ -281,12 +326,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     finB = __shfl_sync(TAXI_FULL_MASK, finB, llB);
     __syncwarp();
 
-    const int scoreA = ((int)(finA & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * A.nA;
-    traceback16<H>(a, p0, lane, trace, 0, A.xb, A.yb, A.nA, A.nB, 3 - (int)(finA & 3u), scoreA);
-    if (p1 != p0) {
-        const int scoreB = ((int)(finB & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * B.nA;
-        traceback16<H>(a, p1, lane, trace, 1, B.xb, B.yb, B.nA, B.nB, 3 - (int)(finB & 3u), scoreB);
-    }
+    Walk wa = walk_start(a, p0, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta);
+    Walk wb = walk_start(a, p1, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta);
+    traceback_two<H>(a, lane, trace, 0, wa, wb, p1 != p0);
 }
 
 #ifndef PAIR16_FMA_ADDS
@@ -406,6 +448,13 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     uint8_t* tbase = trace + (size_t)lane * HB;
     const int tA = A.nB - 1 + (31 - l0), tB = B.nB - 1 + (31 - l0);   // steps at which lane 31 finishes column nB
     int t = 0;
+    // symbols of y are fetched one step ahead so that the load latency hides behind a whole step
+    auto fetch_b = [&](int jj, uint32_t& o0, uint32_t& o1) {
+        o0 = (jj >= 1 && jj <= A.nB) ? (uint32_t)__ldg(A.yc + jj - 1) : PAD;
+        o1 = (jj >= 1 && jj <= B.nB) ? (uint32_t)__ldg(B.yc + jj - 1) : PAD;
+    };
+    uint32_t nb0, nb1;
+    fetch_b(0 - (lane - l0) + 1, nb0, nb1);
 #pragma unroll 1
     for (int seg = 0; seg < 3; ++seg) {
         const int tend = (seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps);
@@ -415,9 +464,9 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
             uint32_t rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
             if (lane == 0) { rX = NEG2; rH = NEG2; }   // nothing above slot 0
             const bool active = live && j >= 1 && j <= nBmax;
+            const uint32_t b0 = nb0, b1 = nb1;
+            fetch_b(j + 1, nb0, nb1);
             if (active) {
-                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
-                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
                 const uint32_t b2 = b0 | (b1 << 8);
                 const uint32_t lutA = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(0, (int)b0, 0, lane)) : 0u;
                 const uint32_t lutB = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(1, (int)b1, 0, lane)) : 0u;
@@ -477,12 +526,13 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-    const int scoreA = ((int)(finA & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * A.nA;
-    traceback16<H>(a, p0, lane, trace, 0, A.xb, A.yb, A.nA, A.nB, 3 - (int)(finA & 3u), scoreA, offA, l0);
-    if (p1 != p0) {
-        const int scoreB = ((int)(finB & 0xFFF0u) - (int)F16_BIAS) / 16 + f.beta * B.nA;
-        traceback16<H>(a, p1, lane, trace, 1, B.xb, B.yb, B.nA, B.nB, 3 - (int)(finB & 3u), scoreB, offB, l0);
-    }
+#ifdef PAIR16_SKIP_TRACEBACK   // experiment only: DP-only throughput
+    if (lane == 0 && a.counts) { a.counts[4 * p0] = (int)finA; a.counts[4 * p1 + 1] = (int)finB; }
+    return;
+#endif
+    Walk wa = walk_start(a, p0, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta);
+    Walk wb = walk_start(a, p1, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta);
+    traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 
 #ifndef PAIR16_WPB
