@@ -132,9 +132,9 @@ void taxi_host_free(void* p);
  * Options: "force_general" = 1 routes every alignment through the general int32 kernel
  * (the packed 16-bit fast path is only taken when it is provably exact for the score set and
  * lengths; this switch exists so tests can compare the two); "force_top" = 1 keeps the packed
- * kernel on its top-aligned variant, "force_nolut" = 1 disables its shared-memory substitution
- * table.  taxi_last_kernel() reports which kernel the last alignment call used: 32 = gotoh_warp
- * (int32); gotoh_pair16: 16 = top-aligned, 17 = bottom-aligned, 18 = bottom-aligned + table.
+ * kernel on its top-aligned variant.  taxi_last_kernel() reports which kernel the last alignment
+ * call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 top-aligned, 17 = gotoh_pair16
+ * bottom-aligned.
  */
 int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
 int taxi_last_kernel(taxi_ctx* ctx);

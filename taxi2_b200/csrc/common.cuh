@@ -28,7 +28,6 @@ struct Fast16 {
     int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties: internal open/extend, end open/extend
     int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties
     int32_t beta;                      // min(match, mismatch), unscaled
-    uint32_t one;                      // = 1, opaque to the compiler: multiplier that keeps packed adds on the fma pipe (IMAD)
 };
 
 struct AlignArgs {

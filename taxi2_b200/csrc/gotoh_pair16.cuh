@@ -67,9 +67,12 @@ template <int H> struct Pair16Geom {
 };
 
 // Warp-parallel first-path traceback over the 4-bit codes.  The walk is a chain of dependent
-// loads (each iteration needs the previous one's outcome), so the walks of the two pairs a warp
-// has just aligned are advanced in lockstep: both windows' loads are issued before either is
-// consumed, which halves the exposed memory latency.
+// loads (each iteration needs the previous one's outcome).  Two measures hide that latency:
+//  * the walks of the two pairs a warp has just aligned advance in lockstep, both windows' loads
+//    being issued before either is consumed;
+//  * every fetch also loads, speculatively, the window that follows if the current run continues
+//    for all 32 lanes (the common case inside long diagonal runs); when it does, the next
+//    iteration starts from data that is already in registers.
 struct Walk {
     const uint8_t* x; const uint8_t* y;   // ASCII of the two sequences
     long long p;                          // pair index (outputs)
@@ -79,24 +82,36 @@ struct Walk {
     bool seen;
     int64_t wpos;                         // write cursor of the gapped strings
     int score;
-    int tb, ca, cb; bool valid;           // the window element this lane fetched
+    int tb, ca, cb; bool valid;           // the window element this lane holds
+    int stb, sca, scb; bool svalid;       // ... and the speculative next window
+    bool have;                            // speculative data is the current window
 };
+
+template <int H>
+__device__ __forceinline__ void walk_load(const Walk& w, int lane, const uint8_t* trace, int l0, int i, int j,
+                                          int& tb, int& ca, int& cb, bool& valid)
+{
+    constexpr int HB = Pair16Geom<H>::HB;
+    const int di = (w.state != 2), dj = (w.state != 1);
+    const int ii = i - lane * di, jj = j - lane * dj;
+    valid = i > 0 && j > 0 && ii >= 1 && jj >= 1;
+    tb = 0; ca = 0; cb = 0;
+    if (valid) {
+        const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
+        const int l = slot / H, r = slot % H;
+        tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + w.half);
+        ca = (int)__ldg(w.x + ii - 1);
+        cb = (int)__ldg(w.y + jj - 1);
+    }
+}
 
 template <int H>
 __device__ __forceinline__ void walk_fetch(Walk& w, int lane, const uint8_t* trace, int l0)
 {
-    constexpr int HB = Pair16Geom<H>::HB;
     const int di = (w.state != 2), dj = (w.state != 1);
-    const int ii = w.i - lane * di, jj = w.j - lane * dj;
-    w.valid = w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1;
-    w.tb = 0; w.ca = 0; w.cb = 0;
-    if (w.valid) {
-        const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
-        const int l = slot / H, r = slot % H;
-        w.tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + w.half);
-        w.ca = (int)__ldg(w.x + ii - 1);
-        w.cb = (int)__ldg(w.y + jj - 1);
-    }
+    if (w.have) { w.tb = w.stb; w.ca = w.sca; w.cb = w.scb; w.valid = w.svalid; }   // warp-uniform
+    else walk_load<H>(w, lane, trace, l0, w.i, w.j, w.tb, w.ca, w.cb, w.valid);
+    walk_load<H>(w, lane, trace, l0, w.i - 32 * di, w.j - 32 * dj, w.stb, w.sca, w.scb, w.svalid);
 }
 
 __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int lane)
@@ -142,6 +157,7 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     }
     w.wpos -= V;
     w.i -= V * di; w.j -= V * dj;
+    w.have = (V == 32) && (next == state);   // the speculative window is exactly the next one
     w.state = next;
 }
 
@@ -177,6 +193,7 @@ __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, cons
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - (int)F16_BIAS) / 16 + beta * nA;
     w.tb = w.ca = w.cb = 0; w.valid = false;
+    w.stb = w.sca = w.scb = 0; w.svalid = false; w.have = false;
     return w;
 }
 
@@ -331,69 +348,19 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     traceback_two<H>(a, lane, trace, 0, wa, wb, p1 != p0);
 }
 
-#ifndef PAIR16_FMA_ADDS
-#define PAIR16_FMA_ADDS 0
-#endif
-
-__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t a, uint32_t b, uint32_t one)
-{
-    // a + b issued as IMAD a*one+b (fma pipe; `one` is a kernel parameter equal to 1, so ptxas
-    // cannot fold it back into an ALU add): the alu pipe is the bottleneck of this kernel
-#if PAIR16_FMA_ADDS
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
-    return r;
-#else
-    (void)one;
-    return a + b;
-#endif
-}
-
 // Bottom-aligned variant: the rows of each pair are shifted (per half) so that row nA always sits
 // in the last register slot of lane 31.  The only rows with special (end-gap) constants are then
 // row nA -- a fixed slot -- and the border row 0, which is kept as an ordinary row whose Iy chain
 // reproduces the leading end gap by itself (requires internal extend == end extend, checked on
 // the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
 // infinity".
-// With LUT = true the substitution increments come from a per-warp shared-memory table
-// lut[half][symbol b][row slot][lane] (u16: 16*(match-beta) where the row's symbol equals b, else
-// 0) instead of the LOP3 + PRMT pair: two LDS.U16 (load/store pipe, otherwise idle) and one IMAD
-// replace two alu-pipe instructions per row, which is the pipe this kernel saturates.  Needs the
-// plain 5-symbol alphabet (A C G T N; symbol 5 = padding past the end of y).
-//
-// Layout: every lane keeps its entries in "its own" bank -- u16 entry e = b*HP + r of a half lives
-// in 32-bit word (e/2)*32 + lane, halfword e&1 -- so the LDS.U16 of a warp never conflict, whatever
-// symbols the 32 lanes look up (HP = H rounded up to even keeps the address affine in r).
-__device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr, uint32_t epoch)
-{
-    // explicit 16-bit shared load: the sub-word select is free in the load/store unit, whereas the
-    // compiler would fuse neighbouring entries into one LDS.32 and split them with alu-pipe PRMTs.
-    // Not volatile, so the scheduler may hoist it ahead of its use; `epoch` (the work-unit index)
-    // is a fake input that makes loads of different units distinct values for the optimiser.
-    uint32_t v;
-    asm("ld.shared.u16 %0, [%1]; // %2" : "=r"(v) : "r"(smem_addr), "r"(epoch));
-    return v;
-}
-
-constexpr int LUT_SYMBOLS = 6;
-template <int H> struct Pair16Lut {
-    static constexpr int HP = (H + 1) / 2 * 2;
-    static constexpr int HALF_U16 = LUT_SYMBOLS * HP * 32;     // u16 entries per half
-    static constexpr int BYTES = 2 * HALF_U16 * 2;
-    __device__ static __forceinline__ int index(int half, int b, int r, int lane)
-    {
-        const int e = b * HP + r;
-        return half * HALF_U16 + ((e >> 1) * 32 + lane) * 2 + (e & 1);
-    }
-};
-
-template <int H, bool LUT>
-__device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace,
-                                                 uint16_t* lut)
+template <int H>
+__device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
 {
     constexpr int HB = Pair16Geom<H>::HB;
     constexpr int WORDS = Pair16Geom<H>::WORDS;
     constexpr int SL = 32 * H;
+    constexpr uint32_t PAD = 7u;                         // symbol past the end of y: matches nothing
     const Fast16& f = a.f16;
     const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
     const int offA = SL - A.nA, offB = SL - B.nA;        // slot of row 1; row 0 sits in slot off-1
@@ -416,13 +383,6 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
         const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
         const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
         a2[r] = c0 | (c1 << 8);
-        if constexpr (LUT) {
-#pragma unroll
-            for (int c = 0; c < LUT_SYMBOLS; ++c) {
-                lut[Pair16Lut<H>::index(0, c, r, lane)] = (uint16_t)((c0 == (uint32_t)c) ? f.D16 : 0);
-                lut[Pair16Lut<H>::index(1, c, r, lane)] = (uint16_t)((c1 == (uint32_t)c) ? f.D16 : 0);
-            }
-        }
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
         // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
         const uint32_t y0 = F16_BIAS - f.PeoY + 8u;
@@ -430,24 +390,19 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     }
     const int itA = lane * H - offA, itB = lane * H - offB;   // row above my top slot
     uint32_t Hd_saved = pack16(col0_H(itA), col0_H(itB));
-    // Iy constants: internal everywhere except the very last slot (row nA of both pairs)
+    // Iy constants: internal everywhere except the very last slot (row nA of both pairs).  The
+    // "subtract a packed non-negative constant" steps are written as x + (-c) with a full 32-bit
+    // negation of the packed constant (no borrow can cross the halves, see the header comment).
     const uint32_t ncYMi = pack16((uint32_t)(5 - f.PoY), (uint32_t)(5 - f.PoY));
-    // the "subtract a packed non-negative constant" steps are done as x + (-c) with a full 32-bit
-    // negation of the packed constant (no borrow can cross the halves, see the header comment)
-    const uint32_t one = f.one;
     const uint32_t cYYi = 0u - pack16((uint32_t)(f.PeY + 1), (uint32_t)(f.PeY + 1));
     const uint32_t ncYMl = (lane == 31) ? pack16((uint32_t)(5 - f.PeoY), (uint32_t)(5 - f.PeoY)) : ncYMi;
     const uint32_t cYYl = (lane == 31) ? 0u - pack16((uint32_t)(f.PeeY + 1), (uint32_t)(f.PeeY + 1)) : cYYi;
     const uint32_t ncXMi = pack16((uint32_t)(1 - f.PoX), (uint32_t)(1 - f.PoX));
     const uint32_t cXXi = 0u - pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
 
-    if constexpr (LUT) __syncwarp();
-    const uint32_t epoch = (uint32_t)p0;
-    constexpr uint32_t PAD = LUT ? 5u : 7u;   // symbol past the end of y: matches nothing
     uint32_t outX = NEG2, outH = NEG2, finA = 0, finB = 0;
     uint8_t* tbase = trace + (size_t)lane * HB;
     const int tA = A.nB - 1 + (31 - l0), tB = B.nB - 1 + (31 - l0);   // steps at which lane 31 finishes column nB
-    int t = 0;
     // symbols of y are fetched one step ahead so that the load latency hides behind a whole step
     auto fetch_b = [&](int jj, uint32_t& o0, uint32_t& o1) {
         o0 = (jj >= 1 && jj <= A.nB) ? (uint32_t)__ldg(A.yc + jj - 1) : PAD;
@@ -455,8 +410,9 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     };
     uint32_t nb0, nb1;
     fetch_b(0 - (lane - l0) + 1, nb0, nb1);
+    int t = 0;
 #pragma unroll 1
-    for (int seg = 0; seg < 3; ++seg) {
+    for (int seg = 0; seg < 3; ++seg) {   // three segments: see align_two()
         const int tend = (seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps);
         for (; t < tend; ++t) {
             const int j = t - (lane - l0) + 1;
@@ -468,15 +424,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
             fetch_b(j + 1, nb0, nb1);
             if (active) {
                 const uint32_t b2 = b0 | (b1 << 8);
-                const uint32_t lutA = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(0, (int)b0, 0, lane)) : 0u;
-                const uint32_t lutB = LUT ? (uint32_t)__cvta_generic_to_shared(lut + Pair16Lut<H>::index(1, (int)b1, 0, lane)) : 0u;
-                auto sub_of = [&](int r) -> uint32_t {
-                    if constexpr (LUT) {
-                        const uint32_t o = ((r >> 1) * 64 + (r & 1)) * 2;   // byte offset of row r from row 0 (b*HP is even)
-                        return lds_u16(lutB + o, epoch) * 65536u + lds_u16(lutA + o, epoch);
-                    }
-                    else return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u));
-                };
+                auto sub_of = [&](int r) -> uint32_t { return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u)); };
                 uint32_t ncXM = ncXMi, cXX = cXXi;
                 if (j == A.nB || j == B.nB) {   // a vertical gap in a pair's last column is an end gap
                     const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
@@ -487,20 +435,19 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 uint32_t Xin = rX;
                 uint32_t tw[WORDS];
                 uint32_t tprev = 0;
-                uint32_t Mr = add_fma_pipe(sub_of(0), Hd_saved, one);
+                uint32_t Mr = Hd_saved + sub_of(0);
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     uint32_t Mr_next = 0;
-                    if (r + 1 < H)   // diagonal term of the next row needs H(i, j-1) before it is overwritten
-                        Mr_next = add_fma_pipe(sub_of(r + 1), Hl[r], one);
+                    if (r + 1 < H) Mr_next = Hl[r] + sub_of(r + 1);   // needs H(i, j-1) before it is overwritten
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
                     const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
                     const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
                     Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
-                    Xin = __viaddmax_u16x2(Mt, ncXM, add_fma_pipe(cXX, Xt, one));
-                    Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, add_fma_pipe((r == H - 1) ? cYYl : cYYi, Yt, one));
+                    Xin = __viaddmax_u16x2(Mt, ncXM, Xt + cXX);
+                    Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt + ((r == H - 1) ? cYYl : cYYi));
                     if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
                     else if (r == H - 1) tw[r >> 1] = __byte_perm(tc, 0u, 0x6420);
                     tprev = tc;
@@ -526,10 +473,6 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-#ifdef PAIR16_SKIP_TRACEBACK   // experiment only: DP-only throughput
-    if (lane == 0 && a.counts) { a.counts[4 * p0] = (int)finA; a.counts[4 * p1 + 1] = (int)finB; }
-    return;
-#endif
     Walk wa = walk_start(a, p0, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta);
     Walk wb = walk_start(a, p1, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta);
     traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
@@ -538,25 +481,16 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
 #ifndef PAIR16_WPB
 #define PAIR16_WPB 4
 #endif
+#ifndef PAIR16_MIN_BLOCKS
+#define PAIR16_MIN_BLOCKS 3   // 168 registers: measured best (fewer blocks or forced spills are both slower)
+#endif
 constexpr int PAIR16_WARPS_PER_BLOCK = PAIR16_WPB;
 
-#ifndef PAIR16_MIN_BLOCKS
-#define PAIR16_MIN_BLOCKS 3
-#endif
-
-#ifdef PAIR16_MAXNREG
-#define PAIR16_BOUNDS __maxnreg__(PAIR16_MAXNREG)
-#else
-#define PAIR16_BOUNDS __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, PAIR16_MIN_BLOCKS)
-#endif
-
-// MODE 0: top-aligned rows; 1: bottom-aligned; 2: bottom-aligned + shared-memory substitution table
+// MODE 0: top-aligned rows; 1: bottom-aligned rows
 template <int H, int MODE>
-__global__ void PAIR16_BOUNDS
+__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, PAIR16_MIN_BLOCKS)
 gotoh_pair16_kernel(const AlignArgs a)
 {
-    extern __shared__ __align__(16) uint8_t pair16_smem[];
-    uint16_t* lut = reinterpret_cast<uint16_t*>(pair16_smem + (size_t)(threadIdx.x >> 5) * Pair16Lut<H>::BYTES);
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * PAIR16_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     uint8_t* trace = a.trace + gw * a.trace_per_warp;
@@ -568,8 +502,7 @@ gotoh_pair16_kernel(const AlignArgs a)
         if (u >= units) break;
         const long long p0 = (long long)(2ULL * u);
         const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
-        if constexpr (MODE == 2) align_two_bottom<H, true>(a, p0, p1, lane, trace, lut);
-        else if constexpr (MODE == 1) align_two_bottom<H, false>(a, p0, p1, lane, trace, lut);
+        if constexpr (MODE == 1) align_two_bottom<H>(a, p0, p1, lane, trace);
         else align_two<H>(a, p0, p1, lane, trace);
         __syncwarp();
     }

@@ -86,7 +86,6 @@ struct taxi_ctx {
     DevBuf<uint8_t> d_codebook;
     int force_general = 0;          // option: always use the general int32 kernel
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
-    int force_nolut = 0;            // option: packed kernel without the shared-memory substitution table
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
     DevBuf<uint8_t> trace;
@@ -168,27 +167,20 @@ __global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, int64_t n
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = lut[bytes[k]];
 }
 
-template <int H, int MODE> constexpr int pair16_smem() { return MODE == 2 ? PAIR16_WARPS_PER_BLOCK * Pair16Lut<H>::BYTES : 0; }
-
 template <int H, int MODE> cudaError_t occupancy16(int* blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(gotoh_pair16_kernel<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair16_smem<H, MODE>());
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H, MODE>, PAIR16_WARPS_PER_BLOCK * 32,
-                                                         pair16_smem<H, MODE>());
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H, MODE>, PAIR16_WARPS_PER_BLOCK * 32, 0);
 }
 
 template <int H, int MODE> void launch_pair16(const AlignArgs& a, int grid, cudaStream_t st)
 {
-    gotoh_pair16_kernel<H, MODE><<<grid, PAIR16_WARPS_PER_BLOCK * 32, pair16_smem<H, MODE>(), st>>>(a);
+    gotoh_pair16_kernel<H, MODE><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
 }
 
 #define P16(H, M) {H, occupancy16<H, M>, launch_pair16<H, M>, Pair16Geom<H>::HB}
 const Dispatch kDispatch16[] = {P16(8, 0), P16(12, 0), P16(16, 0), P16(21, 0), P16(24, 0), P16(32, 0)};
 // bottom-aligned rows (needs internal extend == end extend and one spare row slot)
 const Dispatch kDispatch16b[] = {P16(8, 1), P16(12, 1), P16(16, 1), P16(21, 1), P16(24, 1), P16(32, 1)};
-// ... plus the shared-memory substitution table (needs the plain A C G T N alphabet)
-const Dispatch kDispatch16l[] = {P16(8, 2), P16(12, 2), P16(16, 2), P16(21, 2), P16(24, 2), P16(32, 2)};
 #undef P16
 
 // Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
@@ -222,7 +214,7 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     for (const auto& e : kDispatch16) if (32 * e.H >= max_rows + (bottom ? 1 : 0)) { H = e.H; break; }
     if (!H) return false;
     Fast16 f;
-    f.D16 = 16 * D; f.beta = beta; f.one = 1u;
+    f.D16 = 16 * D; f.beta = beta;
     f.PoX = 16 * (beta - io); f.PeX = 16 * (beta - ie); f.PeoX = 16 * (beta - eo); f.PeeX = 16 * (beta - ee);
     f.PoY = -16 * io; f.PeY = -16 * ie; f.PeoY = -16 * eo; f.PeeY = -16 * ee;
     // range: every value of the (padded) DP stays inside the unsigned 16-bit window around the bias
@@ -233,7 +225,7 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     const long long lower = 2 * pen_o + (R + C) * pen_e, upper = (long long)f.D16 * std::min(R, C);
     if (0x8000LL - lower < 0x0800LL + 2 * 2048 || 0x8000LL + upper > 65000) return false;
     *out = f; *H_out = H;
-    *mode_out = !bottom ? 0 : ((c->ncodes <= 5 && !c->force_nolut) ? 2 : 1);
+    *mode_out = bottom ? 1 : 0;
     return true;
 }
 
@@ -247,7 +239,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H, &mode);
     if (!fast) H = pick_H(max_rows);
     const Dispatch* d = nullptr;
-    if (fast) { for (const auto& e : (mode == 2 ? kDispatch16l : (mode == 1 ? kDispatch16b : kDispatch16))) if (e.H == H) d = &e; }
+    if (fast) { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
     else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
     int bps = 0;
     CUDA_TRY(d->occ(&bps));
@@ -757,7 +749,6 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (!c || !key) return fail(TAXI_E_ARG, "null argument");
     if (std::strcmp(key, "force_general") == 0) { c->force_general = value; return TAXI_OK; }
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
-    if (std::strcmp(key, "force_nolut") == 0) { c->force_nolut = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }
 

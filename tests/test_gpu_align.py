@@ -50,10 +50,9 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
     px = np.arange(n, dtype=np.int32)
     want = oracle_batch(xs, ys, px, px, scores)
     kernels = set()
-    for force_general, force_top, force_nolut in ((0, 0, 0), (0, 0, 1), (0, 1, 0), (1, 0, 0)):
+    for force_general, force_top in ((0, 0), (0, 1), (1, 0)):
         engine.set_option("force_general", force_general)
         engine.set_option("force_top", force_top)
-        engine.set_option("force_nolut", force_nolut)
         try:
             engine.set_scores(scores)
             engine.load(xs, 0)
@@ -74,7 +73,6 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
         finally:
             engine.set_option("force_general", 0)
             engine.set_option("force_top", 0)
-            engine.set_option("force_nolut", 0)
     if expect_fast is True:
         assert 16 in kernels, "packed fast path was expected to be eligible"
     if expect_fast is False:

@@ -1,5 +1,5 @@
 """Quick device-side throughput probe (not the bench contract): GCUPS of one rect launch.
-usage: quick_perf.py [n] [option=value ...]   e.g.  quick_perf.py 1024 force_nolut=1"""
+usage: quick_perf.py [n] [option=value ...]   e.g.  quick_perf.py 1024 force_top=1"""
 import json
 import sys
 import time
