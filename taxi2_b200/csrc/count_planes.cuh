@@ -10,26 +10,33 @@
 //   R      : "real" mask (A/C/G/T)
 //   G      : gap mask ('-')
 // Columns past a sequence's end have R = G = 0, which is exactly "truncate to the shorter".
+// The planes are stored plane-major with the sequence index fastest ([4][W][n]), so a warp whose
+// threads hold consecutive sequences reads every plane word with one coalesced transaction.
 #pragma once
 #include "common.cuh"
 
 namespace taxi {
 
 struct Planes {
-    const uint32_t* w;   // [nseq][4][W] words: b0, b1, R, G
+    const uint32_t* w;   // [4][W][nseq] words (plane-major, sequence fastest): b0, b1, R, G
     int32_t W;           // words per plane
     int32_t nseq;
+    __device__ __forceinline__ uint32_t at(int plane, int word, int seq) const
+    {
+        return __ldg(w + ((size_t)plane * W + word) * nseq + seq);
+    }
 };
 
-// one thread per sequence: bytes -> planes.  Each thread walks its own sequence; the byte loads
-// of a warp are scattered, but this kernel runs once per load (O(N*L)) and is not on the O(N^2) path.
+// one thread per (sequence, word): bytes -> planes.  Consecutive threads take consecutive
+// sequences so the plane words are written coalesced; the byte reads of a warp are scattered, but
+// this kernel runs once per load (O(N*L)) and is not on the O(N^2) path.
 __global__ void pack_planes_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ off,
                                    int32_t nseq, int32_t W, uint32_t* __restrict__ out)
 {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)nseq * W;
     if (gid >= total) return;
-    const int seq = (int)(gid / W), w = (int)(gid % W);
+    const int w = (int)(gid / nseq), seq = (int)(gid % nseq);
     const int64_t o = off[seq];
     const int len = (int)(off[seq + 1] - o);
     uint32_t b0 = 0, b1 = 0, R = 0, G = 0;
@@ -43,42 +50,32 @@ __global__ void pack_planes_kernel(const uint8_t* __restrict__ bytes, const int6
             else if (c == 4) G |= 1u << k;
         }
     }
-    uint32_t* dst = out + (size_t)seq * 4 * W;
-    dst[w] = b0; dst[W + w] = b1; dst[2 * W + w] = R; dst[3 * W + w] = G;
+    const size_t plane = (size_t)W * nseq;
+    uint32_t* dst = out + (size_t)w * nseq + seq;
+    dst[0] = b0; dst[plane] = b1; dst[2 * plane] = R; dst[3 * plane] = G;
 }
 
 struct CountArgs {
     Planes x, y;
     const int32_t* px; const int32_t* py;   // explicit list or nullptr (rect)
-    int32_t x0, y0, ny;
+    int32_t x0, y0, nx, ny;
     long long npairs;
     int32_t* counts;   // [npairs][4] or nullptr
     double* metrics;   // [npairs][4] or nullptr
 };
 
-// One thread per pair.  In rect mode consecutive threads take consecutive y for the same x, so
-// the x planes are a warp-broadcast load and the results are written fully coalesced (16 B and
-// 32 B per pair); the y planes of a tile stay L1/L2 resident (the whole plane set is a few MB).
-__global__ void __launch_bounds__(256) count_planes_kernel(const CountArgs a)
-{
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.npairs) return;
-    int xi, yi;
-    if (a.px) { xi = a.px[p]; yi = a.py[p]; }
-    else { xi = a.x0 + (int)(p / a.ny); yi = a.y0 + (int)(p % a.ny); }
-    const int W = min(a.x.W, a.y.W);
-    const uint32_t* __restrict__ X = a.x.w + (size_t)xi * 4 * a.x.W;
-    const uint32_t* __restrict__ Y = a.y.w + (size_t)yi * 4 * a.y.W;
-    const int WX = a.x.W, WY = a.y.W;
-    int same = 0, ts = 0, tv = 0, gapc = 0, pend = 0;
-    bool seen = false;
-    for (int w = 0; w < W; ++w) {
-        const uint32_t xr = __ldg(X + 2 * WX + w), yr = __ldg(Y + 2 * WY + w);
+// running state of one pair's scan (columns in order): the trim-to-first/last-both-real rule
+struct CountState {
+    int same, ts, tv, gapc, pend;
+    bool seen;
+    __device__ __forceinline__ void init() { same = ts = tv = gapc = pend = 0; seen = false; }
+    __device__ __forceinline__ void word(uint32_t x0, uint32_t x1, uint32_t xr, uint32_t xg,
+                                         uint32_t y0, uint32_t y1, uint32_t yr, uint32_t yg)
+    {
         const uint32_t both = xr & yr;
-        const uint32_t gapw = (__ldg(X + 3 * WX + w) & yr) | (xr & __ldg(Y + 3 * WY + w));
+        const uint32_t gapw = (xg & yr) | (xr & yg);
         if (both) {
-            const uint32_t d0 = __ldg(X + w) ^ __ldg(Y + w);
-            const uint32_t d1 = __ldg(X + WX + w) ^ __ldg(Y + WY + w);
+            const uint32_t d0 = x0 ^ y0, d1 = x1 ^ y1;
             tv += __popc(both & d1);
             ts += __popc(both & d0 & ~d1);
             same += __popc(both & ~(d0 | d1));
@@ -93,14 +90,74 @@ __global__ void __launch_bounds__(256) count_planes_kernel(const CountArgs a)
             pend += __popc(gapw);
         }
     }
-    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);
-    if (a.metrics) {
-        double m[4];
-        metrics_from_counts(same, ts, tv, gapc, m);
-        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
-        dst[0] = make_double2(m[0], m[1]);
-        dst[1] = make_double2(m[2], m[3]);
+    __device__ __forceinline__ void store(const CountArgs& a, long long p) const
+    {
+        if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);
+        if (a.metrics) {
+            double m[4];
+            metrics_from_counts(same, ts, tv, gapc, m);
+            double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
+            dst[0] = make_double2(m[0], m[1]);
+            dst[1] = make_double2(m[2], m[3]);
+        }
     }
+};
+
+// Rectangle mode.  A block owns COUNT_TY consecutive y columns (one per thread) and walks the x
+// rows of its slab in groups of COUNT_RX: the y words of a thread are loaded once per group
+// (coalesced across the warp, plane-major layout) and reused for COUNT_RX pairs whose x words come
+// from shared memory as warp broadcasts.  Results are written coalesced, 16 B + 32 B per pair.
+constexpr int COUNT_TY = 256;
+constexpr int COUNT_RX = 8;
+constexpr int COUNT_SLAB = 64;   // x rows staged in shared memory per block
+
+__global__ void __launch_bounds__(COUNT_TY, 2) count_rect_kernel(const CountArgs a)
+{
+    extern __shared__ uint32_t xs[];   // [COUNT_SLAB][4][W]
+    const int W = min(a.x.W, a.y.W);
+    const int yj = blockIdx.x * COUNT_TY + threadIdx.x;          // column inside the rectangle
+    const int xbase = blockIdx.y * COUNT_SLAB;                   // first row of the slab
+    const int rows = min(COUNT_SLAB, a.nx - xbase);
+    for (int k = threadIdx.x; k < rows * 4 * W; k += COUNT_TY) {
+        const int r = k / (4 * W), pw = k % (4 * W);
+        xs[k] = a.x.at(pw / W, pw % W, a.x0 + xbase + r);
+    }
+    __syncthreads();
+    if (yj >= a.ny) return;
+    const int ys = a.y0 + yj;
+    for (int g = 0; g < rows; g += COUNT_RX) {
+        CountState st[COUNT_RX];
+#pragma unroll
+        for (int k = 0; k < COUNT_RX; ++k) st[k].init();
+        for (int w = 0; w < W; ++w) {
+            const uint32_t y0 = a.y.at(0, w, ys), y1 = a.y.at(1, w, ys), yr = a.y.at(2, w, ys), yg = a.y.at(3, w, ys);
+#pragma unroll
+            for (int k = 0; k < COUNT_RX; ++k) {
+                if (g + k < rows) {
+                    const uint32_t* xw = xs + (size_t)(g + k) * 4 * W + w;
+                    st[k].word(xw[0], xw[W], xw[2 * W], xw[3 * W], y0, y1, yr, yg);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < COUNT_RX; ++k)
+            if (g + k < rows) st[k].store(a, (long long)(xbase + g + k) * a.ny + yj);
+    }
+}
+
+// Explicit pair list: one thread per pair.
+__global__ void __launch_bounds__(256) count_pairs_kernel(const CountArgs a)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.npairs) return;
+    const int xi = a.px[p], yi = a.py[p];
+    const int W = min(a.x.W, a.y.W);
+    CountState st;
+    st.init();
+    for (int w = 0; w < W; ++w)
+        st.word(a.x.at(0, w, xi), a.x.at(1, w, xi), a.x.at(2, w, xi), a.x.at(3, w, xi),
+                a.y.at(0, w, yi), a.y.at(1, w, yi), a.y.at(2, w, yi), a.y.at(3, w, yi));
+    st.store(a, p);
 }
 
 // versus_reference.py:184-188 / decontaminate.py:258-264: first minimum per query row, NaN skipped.

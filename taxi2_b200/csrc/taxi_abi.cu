@@ -652,8 +652,17 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
     CUDA_TRY(c->status.reserve(1));
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    const long long blocks = (a.npairs + 255) / 256;
-    count_planes_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+    if (a.px) {
+        const long long blocks = (a.npairs + 255) / 256;
+        count_pairs_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
+    } else {
+        const int W = std::min(X.W, Y.W);
+        const size_t smem = (size_t)COUNT_SLAB * 4 * W * sizeof(uint32_t);
+        if (smem > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
+        CUDA_TRY(cudaFuncSetAttribute(count_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((a.ny + COUNT_TY - 1) / COUNT_TY), (unsigned)((a.nx + COUNT_SLAB - 1) / COUNT_SLAB));
+        count_rect_kernel<<<grid, COUNT_TY, smem, c->stream>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
@@ -668,10 +677,10 @@ int taxi_count_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
-    if (npairs > 0x7fffffffLL * 256) return fail(TAXI_E_ARG, "rectangle too large for one launch");
+    if ((nx + COUNT_SLAB - 1) / COUNT_SLAB > 65535) return fail(TAXI_E_ARG, "rectangle too tall for one launch (max %d rows)", 65535 * COUNT_SLAB);
     CUDA_TRY(cudaSetDevice(c->device));
     CountArgs a{};
-    a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
+    a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.nx = nx; a.ny = ny; a.npairs = npairs;
     a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
     a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
     return enqueue_count(c, a);
