@@ -315,13 +315,13 @@ def main() -> None:
         achieved = cells_per_launch * OPS_PER_CELL / launch_s
         # traceback codes written per cell: packed kernel 48 B per (lane, column) = 42 cells;
         # general kernel 24 B per 21 cells
-        trace_bytes_per_cell = 48.0 / 42.0 if kernel_id == 16 else 24.0 / 21.0
-        kernel_name = "gotoh_pair16_kernel<21>" if kernel_id == 16 else "gotoh_warp_kernel<21>"
+        trace_bytes_per_cell = 48.0 / 42.0 if kernel_id in (16, 17) else 24.0 / 21.0
+        kernel_name = {16: "gotoh_pair16_kernel<21,0>", 17: "gotoh_pair16_kernel<21,1>"}.get(kernel_id, "gotoh_warp_kernel<21>")
         cpu = cpu_oracle_throughput(data[: off[4096]], off[:4097], args.cpu_seconds)
         line = dict(
             metric="aligned_pairs_per_sec", value=value, unit="pairs/s", gcups=gcups,
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps,
-            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u16x2" if kernel_id == 16 else "int32", data="synthetic",
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u16x2" if kernel_id in (16, 17) else "int32", data="synthetic",
             config=workload_config(world),
             roofline=dict(
                 bound="int32_alu", kernel=kernel_name, achieved=achieved / 1e9, peak=peak / 1e9, unit="Gop/s",

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -241,8 +242,15 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     const Dispatch* d = nullptr;
     if (fast) { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
     else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
+    // occupancy of each kernel variant is queried once per process
+    static std::map<const Dispatch*, int> occupancy_cache;
     int bps = 0;
-    CUDA_TRY(d->occ(&bps));
+    auto hit = occupancy_cache.find(d);
+    if (hit != occupancy_cache.end()) bps = hit->second;
+    else {
+        CUDA_TRY(d->occ(&bps));
+        occupancy_cache[d] = bps;
+    }
     if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
     const long long SL = 32LL * H;
     const long long nstripes = fast ? 1 : (max_rows + SL - 1) / SL;
@@ -252,10 +260,11 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     c->last_kernel = fast ? 16 + mode : 32;
     a.f16 = f16;
     // resident warps, capped by pairs and by a trace-arena budget of half the free memory
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     long long warps = (long long)c->sms * bps * GOTOH_WARPS_PER_BLOCK;
-    const long long budget = (long long)((free_b + c->trace.cap) / 2);
+    size_t free_b = 0, total_b = 0;
+    if ((long long)c->trace.cap >= warps * per_warp) free_b = 0;   // arena already large enough: no query
+    else CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const long long budget = std::max<long long>((long long)c->trace.cap, (long long)((free_b + c->trace.cap) / 2));
     if (per_warp > budget) return fail(TAXI_E_NOMEM, "one pair needs %lld B of traceback arena, only %lld B available", per_warp, budget);
     warps = std::min(warps, std::max(1LL, budget / per_warp));
     warps = std::min(warps, work_units);
