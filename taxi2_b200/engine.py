@@ -202,6 +202,39 @@ class Engine:
         """32 = general int32 kernel, 16 = packed 16-bit two-pairs-per-warp kernel."""
         return int(self._lib.taxi_last_kernel(self._ctx))
 
+    def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None) -> dict:
+        """versusReference at scale (BASELINE config C4): for every row sequence of set 0 the FIRST
+        minimum of metric column `metric` over all of set 1 (versus_reference.py:184-188), plus all
+        four metrics and the counts of that winning pair.  The nx x ny matrix never leaves the
+        device: row tiles are aligned into a device buffer, reduced by the argmin kernel, and only
+        the winners come back.  index = -1 where a query has no defined distance."""
+        import torch
+
+        nx, ny = self.n[0], self.ny
+        if rows_per_tile is None:
+            rows_per_tile = max(1, min(nx, (1 << 22) // max(ny, 1)))
+        dev = torch.device("cuda", self.device)
+        d_metrics = torch.empty((rows_per_tile * ny, 4), dtype=torch.float64, device=dev)
+        d_counts = torch.empty((rows_per_tile * ny, 4), dtype=torch.int32, device=dev)
+        index = np.full(nx, -1, dtype=np.int32)
+        best = np.full((nx, 4), np.nan, dtype=np.float64)
+        counts = np.zeros((nx, 4), dtype=np.int32)
+        for x0 in range(0, nx, rows_per_tile):
+            rows = min(rows_per_tile, nx - x0)
+            if align:
+                self.align_rect_device(x0, rows, 0, ny, 0, d_counts.data_ptr(), d_metrics.data_ptr())
+            else:
+                self.count_rect_device(x0, rows, 0, ny, d_counts.data_ptr(), d_metrics.data_ptr())
+            self.sync()
+            idx, _ = self.argmin_rows_device(d_metrics.data_ptr(), rows, ny, metric)
+            index[x0:x0 + rows] = idx
+            ok = np.nonzero(idx >= 0)[0]
+            if len(ok):
+                flat = torch.from_numpy((ok.astype(np.int64) * ny + idx[ok].astype(np.int64))).to(dev)
+                best[x0 + ok] = d_metrics.index_select(0, flat).cpu().numpy()
+                counts[x0 + ok] = d_counts.index_select(0, flat).cpu().numpy()
+        return dict(index=index, metrics=best, counts=counts)
+
     def sync(self) -> None:
         N.check(self._lib.taxi_sync(self._ctx))
 

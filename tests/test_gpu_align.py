@@ -231,3 +231,48 @@ def test_prealigned_counts(engine):
         for j in range(50):
             c = oracle.count(xs[i], ys[j]) or (0, 0, 0, 0)
             assert tuple(rect["counts"][i, j]) == tuple(c)
+
+
+def test_full_size_tile_properties(engine):
+    """BASELINE C3 geometry (650 bp, 384 x 384 ordered pairs = 6.2e10 cells): too large for the CPU
+    oracle, so check size-independent properties -- the three kernel variants agree bit for bit,
+    the diagonal is exact identity, counts are bounded by the lengths, and a sampled subset matches
+    the oracle."""
+    seqs = coi_like(384, seed=650)
+    n = len(seqs)
+    lens = np.array([len(s) for s in seqs])
+    results = {}
+    for name, opts in (("bottom", (0, 0)), ("top", (0, 1)), ("general", (1, 0))):
+        engine.set_option("force_general", opts[0])
+        engine.set_option("force_top", opts[1])
+        try:
+            engine.set_scores(None)
+            engine.load(seqs, 0)
+            results[name] = engine.align_rect(0, n, 0, n)
+            results[name]["kernel"] = engine.last_kernel
+        finally:
+            engine.set_option("force_general", 0)
+            engine.set_option("force_top", 0)
+    assert (results["bottom"]["kernel"], results["top"]["kernel"], results["general"]["kernel"]) == (17, 16, 32)
+    ref = results["general"]
+    for name in ("bottom", "top"):
+        assert np.array_equal(results[name]["score"], ref["score"])
+        assert np.array_equal(results[name]["counts"], ref["counts"])
+        assert np.array_equal(results[name]["metrics"], ref["metrics"], equal_nan=True)
+    counts, score = ref["counts"], ref["score"]
+    diag = np.arange(n)
+    real = np.array([sum(c in b"ACGT" for c in s) for s in seqs])
+    assert np.array_equal(counts[diag, diag, 0], real) and not counts[diag, diag, 1:].any()
+    assert np.array_equal(score[diag, diag], lens)                      # all matches (N matches N)
+    assert np.all(ref["metrics"][diag, diag] == 0.0)
+    compared = counts[..., :3].sum(-1)
+    assert np.all(compared <= np.minimum(lens[:, None], lens[None, :]))
+    assert np.all(counts[..., 3] <= lens[:, None] + lens[None, :])
+    assert np.all(score <= np.minimum(lens[:, None], lens[None, :]))
+    rng = np.random.default_rng(0)
+    px, py = rng.integers(0, n, 200), rng.integers(0, n, 200)
+    from taxi2_b200.engine import pack_strings
+
+    data, off = pack_strings(seqs)
+    want = oracle.align_count_pairs(data, off, px.astype(np.int32), py.astype(np.int32))
+    assert np.array_equal(score[px, py], want["score"]) and np.array_equal(counts[px, py], want["counts"])

@@ -84,3 +84,29 @@ def test_calculate_batch_matches_single_calls():
     batch = DistanceMetric.calculate_batch(metrics, pairs)
     single = [m.calculate(p.x, p.y) for p in pairs for m in metrics]
     assert batch == single
+
+
+def test_best_matches_first_minimum():
+    """Engine.best_matches = per-query first minimum (versus_reference.py:184-188), on device."""
+    import numpy as np
+
+    from synth import coi_like
+    from taxi2_b200.engine import default_engine
+
+    seqs = coi_like(90, seed=11)
+    queries, refs = seqs[:30], seqs[30:] + [seqs[31], seqs[31]]   # duplicated references: ties -> earliest
+    eng = default_engine()
+    eng.set_scores(None)
+    eng.load(queries, 0)
+    eng.load(refs, 1)
+    full = eng.align_rect(0, len(queries), 0, len(refs), want=("metrics", "counts"))
+    got = eng.best_matches(metric=0, rows_per_tile=7)
+    for q in range(len(queries)):
+        col = full["metrics"][q, :, 0]
+        want = int(np.nanargmin(col))     # numpy's argmin returns the first minimum too
+        assert got["index"][q] == want
+        assert np.array_equal(got["metrics"][q], full["metrics"][q, want], equal_nan=True)
+        assert np.array_equal(got["counts"][q], full["counts"][q, want])
+    eng.load(["NNNN"], 0)
+    eng.load(["ACGT"], 1)
+    assert eng.best_matches()["index"][0] == -1
