@@ -134,7 +134,7 @@ void taxi_host_free(void* p);
  * lengths; this switch exists so tests can compare the two); "force_top" = 1 keeps the packed
  * kernel on its top-aligned variant.  taxi_last_kernel() reports which kernel the last alignment
  * call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 top-aligned, 17 = gotoh_pair16
- * bottom-aligned.
+ * bottom-aligned, 48 = a rectangle whose rows were split by length between the two.
  */
 int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
 int taxi_last_kernel(taxi_ctx* ctx);

@@ -30,6 +30,8 @@ struct Fast16 {
     int32_t beta;                      // min(match, mismatch), unscaled
 };
 
+struct PairIndex { int xi, yi; long long out; };
+
 struct AlignArgs {
     const uint8_t* xb; const int64_t* xoff;   // row set (x): bytes + offsets
     const uint8_t* yb; const int64_t* yoff;   // column set (y)
@@ -37,6 +39,8 @@ struct AlignArgs {
     Fast16 f16;
     const int32_t* px; const int32_t* py;     // explicit pair list, or nullptr for rect mode
     int32_t x0, y0, ny;                       // rect mode: pair p = (x0 + p / ny, y0 + p % ny)
+    const int32_t* xrows;                     // rect mode, optional: row r of the launch is sequence xrows[r] (a subset of the
+                                              // rectangle's rows); results still land at ((x - x0) * ny + y)
     long long npairs;
     ScoreSet sc;
     int32_t* score;                           // [npairs] or nullptr
@@ -49,6 +53,17 @@ struct AlignArgs {
     unsigned long long* counter;              // dynamic work counter
     int* status;                              // sticky error flag
 };
+
+__device__ __forceinline__ PairIndex pair_index(const AlignArgs& a, long long p)
+{
+    PairIndex r;
+    if (a.px) { r.xi = a.px[p]; r.yi = a.py[p]; r.out = p; return r; }
+    const int row = (int)(p / a.ny), col = (int)(p % a.ny);
+    r.xi = a.xrows ? a.xrows[row] : a.x0 + row;
+    r.yi = a.y0 + col;
+    r.out = (long long)(r.xi - a.x0) * a.ny + col;
+    return r;
+}
 
 // 0..3 = A,G,C,T (bit1 = pyrimidine: a transition flips only bit0); 4 = '-'; 5 = missing
 __device__ __forceinline__ int base_class(int c)

@@ -206,15 +206,16 @@ struct PairRef {
     const uint8_t* xb; const uint8_t* yb;   // ASCII (traceback classification / strings)
     const uint8_t* xc; const uint8_t* yc;   // 3-bit codes (DP)
     int nA, nB;
+    long long out;                          // index of this pair's results
 };
 
 __device__ __forceinline__ PairRef pair_ref(const AlignArgs& a, long long p)
 {
-    int xi, yi;
-    if (a.px) { xi = a.px[p]; yi = a.py[p]; }
-    else { xi = a.x0 + (int)(p / a.ny); yi = a.y0 + (int)(p % a.ny); }
+    const PairIndex pi = pair_index(a, p);
+    const int xi = pi.xi, yi = pi.yi;
     const int64_t xo = a.xoff[xi], yo = a.yoff[yi];
     PairRef r;
+    r.out = pi.out;
     r.xb = a.xb + xo; r.yb = a.yb + yo; r.xc = a.xc + xo; r.yc = a.yc + yo;
     r.nA = (int)(a.xoff[xi + 1] - xo);
     r.nB = (int)(a.yoff[yi + 1] - yo);
@@ -334,8 +335,8 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     finB = __shfl_sync(TAXI_FULL_MASK, finB, llB);
     __syncwarp();
 
-    Walk wa = walk_start(a, p0, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta);
-    Walk wb = walk_start(a, p1, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta);
+    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta);
+    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta);
     traceback_two<H>(a, lane, trace, 0, wa, wb, p1 != p0);
 }
 
@@ -464,8 +465,8 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-    Walk wa = walk_start(a, p0, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta);
-    Walk wb = walk_start(a, p1, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta);
+    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta);
+    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta);
     traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 

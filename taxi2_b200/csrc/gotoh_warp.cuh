@@ -57,9 +57,9 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
     constexpr int SL = G::SL;
     const ScoreSet& sc = a.sc;
 
-    int xi, yi;
-    if (a.px) { xi = a.px[p]; yi = a.py[p]; }
-    else { xi = a.x0 + (int)(p / a.ny); yi = a.y0 + (int)(p % a.ny); }
+    const PairIndex pi = pair_index(a, p);
+    const int xi = pi.xi, yi = pi.yi;
+    p = pi.out;   // from here on p only addresses the outputs
     const int64_t xo = a.xoff[xi], yo = a.yoff[yi];
     const uint8_t* __restrict__ x = a.xb + xo;
     const uint8_t* __restrict__ y = a.yb + yo;

@@ -93,7 +93,7 @@ struct taxi_ctx {
     DevBuf<int32_t> bnd;
     DevBuf<unsigned long long> counter;
     DevBuf<int> status;
-    DevBuf<int32_t> d_px, d_py;
+    DevBuf<int32_t> d_px, d_py, d_xrows;
     DevBuf<int32_t> d_score, d_counts;
     DevBuf<double> d_metrics;
     DevBuf<uint8_t> d_alnx, d_alny;
@@ -232,7 +232,7 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
 
 // Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
 // pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.
-int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
+int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool record_start = true, bool reset_work = true)
 {
     Fast16 f16{};
     int H = 0;
@@ -276,12 +276,12 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols)
     CUDA_TRY(c->counter.reserve(1));
     CUDA_TRY(c->status.reserve(1));
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
+    if (reset_work) CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
     a.sc = c->sc;
     a.trace = c->trace.p; a.trace_per_warp = per_warp;
     a.bnd = c->bnd.p; a.bnd_per_warp = bnd_per_warp;
     a.counter = c->counter.p; a.status = c->status.p;
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (record_start) CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     d->launch(a, grid, c->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
@@ -318,7 +318,7 @@ void fill_rect(AlignArgs& a, const taxi_ctx* c, int32_t x0, int32_t y0, int32_t 
     a.xb = X.bytes.p; a.xoff = X.d_off.p;
     a.yb = Y.bytes.p; a.yoff = Y.d_off.p;
     a.xc = X.codes.p; a.yc = Y.codes.p;
-    a.px = a.py = nullptr;
+    a.px = a.py = nullptr; a.xrows = nullptr;
     a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
 }
 
@@ -441,7 +441,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); }
     c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
-    c->d_px.release(); c->d_py.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
+    c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
     c->d_argidx.release(); c->d_argval.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -555,6 +555,39 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
     a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
     c->cells += cells_rect(c->set[0], yset(c), x0, nx, y0, ny);
+
+    // Mixed lengths (BASELINE config C5): the packed kernel only takes rows of up to one stripe.
+    // If only some rows are too long, split the rectangle's rows into two lists -- short rows
+    // go through the packed kernel, long rows through the general one -- instead of letting a
+    // few long sequences pull the whole launch onto the slower kernel.
+    Fast16 f16{};
+    int H = 0, mode = 0;
+    if (!fast16_eligible(c, mr, mc, &f16, &H, &mode)) {
+        const SeqSet& X = c->set[0];
+        const int limit = 32 * 32 - 1;
+        std::vector<int32_t> rows_short, rows_long;
+        int mr_short = 0, mr_long = 0;
+        for (int32_t i = x0; i < x0 + nx; ++i) {
+            const int len = (int)(X.off[i + 1] - X.off[i]);
+            if (len <= limit) { rows_short.push_back(i); mr_short = std::max(mr_short, len); }
+            else { rows_long.push_back(i); mr_long = std::max(mr_long, len); }
+        }
+        if (!rows_short.empty() && !rows_long.empty() && fast16_eligible(c, mr_short, mc, &f16, &H, &mode)) {
+            CUDA_TRY(c->d_xrows.reserve((size_t)nx));
+            CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p, rows_short.data(), rows_short.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p + rows_short.size(), rows_long.data(), rows_long.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));   // the row lists are host vectors about to go out of scope
+            AlignArgs a1 = a, a2 = a;
+            a1.xrows = c->d_xrows.p; a1.npairs = (long long)rows_short.size() * ny;
+            a2.xrows = c->d_xrows.p + rows_short.size(); a2.npairs = (long long)rows_long.size() * ny;
+            if ((rc = enqueue_align(c, a1, mr_short, mc, true, true))) return rc;
+            const int k1 = c->last_kernel;
+            if ((rc = enqueue_align(c, a2, mr_long, mc, false, false))) return rc;
+            c->last_kernel = 48;   // split launch: packed (k1) + general
+            (void)k1;
+            return TAXI_OK;
+        }
+    }
     return enqueue_align(c, a, mr, mc);
 }
 

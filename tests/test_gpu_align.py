@@ -276,3 +276,26 @@ def test_full_size_tile_properties(engine):
     data, off = pack_strings(seqs)
     want = oracle.align_count_pairs(data, off, px.astype(np.int32), py.astype(np.int32))
     assert np.array_equal(score[px, py], want["score"]) and np.array_equal(counts[px, py], want["counts"])
+
+
+def test_mixed_length_rectangle_splits_rows(engine):
+    """BASELINE config C5 geometry: 300-1500 bp sequences in one rectangle.  Rows longer than one
+    packed stripe go through the general kernel, the others through the packed one, and the
+    results land in the usual row-major positions."""
+    rng = np.random.default_rng(5)
+    xs, _ = random_pairs(rng, 24, 300, 1500, sub=0.1, indel=0.02)
+    ys, _ = random_pairs(rng, 10, 300, 1500, sub=0.1, indel=0.02)
+    assert max(map(len, xs)) > 1023 and min(map(len, xs)) < 1023
+    engine.set_scores(None)
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    got = engine.align_rect(0, len(xs), 0, len(ys))
+    assert engine.last_kernel == 48
+    sub = engine.align_rect(3, 11, 2, 7)
+    px, py = np.divmod(np.arange(len(xs) * len(ys)), len(ys))
+    want = oracle_batch(xs, ys, px, py, None)
+    assert np.array_equal(got["score"].ravel(), want["score"])
+    assert np.array_equal(got["counts"].reshape(-1, 4), want["counts"])
+    assert_metrics_close(got["metrics"].reshape(-1, 4), want["metrics"])
+    assert np.array_equal(sub["counts"], got["counts"][3:14, 2:9])
+    assert np.array_equal(sub["score"], got["score"][3:14, 2:9])
