@@ -28,6 +28,8 @@ struct Fast16 {
     int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties: internal open/extend, end open/extend
     int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties
     int32_t beta;                      // min(match, mismatch), unscaled
+    int32_t bias;                      // value representing transformed score 0 (multiple of 16), placed by the host so that
+                                       // every reachable value of the padded DP fits the unsigned 16-bit window
 };
 
 struct PairIndex { int xi, yi; long long out; };

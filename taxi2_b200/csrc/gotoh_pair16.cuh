@@ -25,7 +25,6 @@
 
 namespace taxi {
 
-constexpr uint32_t F16_BIAS = 0x8000u;
 constexpr uint32_t F16_NEG = 0x0800u;          // "minus infinity": below every reachable value
 constexpr uint32_t F16_CLEAN = 0xFFF0FFF0u;
 
@@ -176,14 +175,14 @@ __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lan
 }
 
 __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, const uint8_t* x, const uint8_t* y, int nA, int nB,
-                                           int half, int off, uint32_t fin, int beta)
+                                           int half, int off, uint32_t fin, int beta, int bias)
 {
     Walk w;
     w.x = x; w.y = y; w.p = p; w.i = nA; w.j = nB; w.state = 3 - (int)(fin & 3u);
     w.half = half; w.off = off;
     w.same = w.ts = w.tv = w.gapc = w.pend = 0; w.seen = false;
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
-    w.score = ((int)(fin & 0xFFF0u) - (int)F16_BIAS) / 16 + beta * nA;
+    w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
     w.tb = w.ca = w.cb = 0; w.valid = false;
     return w;
 }
@@ -242,7 +241,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
         const uint32_t c0 = (i <= A.nA) ? (uint32_t)__ldg(A.xc + min(i, A.nA) - 1) : 7u;
         const uint32_t c1 = (i <= B.nA) ? (uint32_t)__ldg(B.xc + min(i, B.nA) - 1) : 7u;
         a2[r] = c0 | (c1 << 8);
-        const uint32_t xb = F16_BIAS - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;   // Ix(i,0), tagged as state Ix
+        const uint32_t xb = (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;   // Ix(i,0), tagged as state Ix
         Hl[r] = pack16(xb, xb);
         Yn[r] = pack16(F16_NEG, F16_NEG);                                        // no Ix->Iy: Iy(i,1) opens from M only
         const int yo0 = (i == A.nA) ? f.PeoY : f.PoY, yo1 = (i == B.nA) ? f.PeoY : f.PoY;
@@ -251,9 +250,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
         cYY[r] = pack16((uint32_t)(ye0 + 1), (uint32_t)(ye1 + 1));    // Iy(tag 1) -> Iy candidate with clean tag
     }
     uint32_t Hd_saved;
-    if (itop == 1) Hd_saved = pack16(F16_BIAS + 3u, F16_BIAS + 3u);   // (0,0): state M
+    if (itop == 1) Hd_saved = pack16((uint32_t)f.bias + 3u, (uint32_t)f.bias + 3u);   // (0,0): state M
     else {
-        const uint32_t v = F16_BIAS - f.PeoX - (uint32_t)(itop - 2) * f.PeeX + 2u;
+        const uint32_t v = (uint32_t)f.bias - f.PeoX - (uint32_t)(itop - 2) * f.PeeX + 2u;
         Hd_saved = pack16(v, v);
     }
     const int llA = (A.nA - 1) / H, rlA = (A.nA - 1) % H;
@@ -276,7 +275,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
             const bool active = live && j >= 1 && j <= nBmax;
             if (lane == 0 && active) {
                 // row 0: only Iy is alive (leading end gap); nothing can open Ix from it
-                const uint32_t y0 = F16_BIAS - f.PeoY - (uint32_t)(j - 1) * f.PeeY + 1u;
+                const uint32_t y0 = (uint32_t)f.bias - f.PeoY - (uint32_t)(j - 1) * f.PeeY + 1u;
                 rH = pack16(y0, y0);
                 rX = pack16(F16_NEG, F16_NEG);
             }
@@ -335,8 +334,8 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     finB = __shfl_sync(TAXI_FULL_MASK, finB, llB);
     __syncwarp();
 
-    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta);
-    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta);
+    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta, f.bias);
+    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta, f.bias);
     traceback_two<H>(a, lane, trace, 0, wa, wb, p1 != p0);
 }
 
@@ -363,8 +362,8 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     const uint32_t NEG2 = pack16(F16_NEG, F16_NEG);
 
     auto col0_H = [&](int i) -> uint32_t {   // H(i, 0): Ix border for i >= 1, M(0,0) for i == 0, dead above
-        if (i >= 1) return F16_BIAS - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;
-        return i == 0 ? F16_BIAS + 3u : F16_NEG;
+        if (i >= 1) return (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;
+        return i == 0 ? (uint32_t)f.bias + 3u : F16_NEG;
     };
 
     uint32_t a2[H], Hl[H], Yn[H];
@@ -377,7 +376,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
         a2[r] = c0 | (c1 << 8);
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
         // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
-        const uint32_t y0 = F16_BIAS - f.PeoY + 8u;
+        const uint32_t y0 = (uint32_t)f.bias - f.PeoY + 8u;
         Yn[r] = pack16(iA == 0 ? y0 : F16_NEG, iB == 0 ? y0 : F16_NEG);
     }
     const int itA = lane * H - offA, itB = lane * H - offB;   // row above my top slot
@@ -465,8 +464,8 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta);
-    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta);
+    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta, f.bias);
+    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta, f.bias);
     traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 

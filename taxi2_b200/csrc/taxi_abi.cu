@@ -218,13 +218,20 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     f.D16 = 16 * D; f.beta = beta;
     f.PoX = 16 * (beta - io); f.PeX = 16 * (beta - ie); f.PeoX = 16 * (beta - eo); f.PeeX = 16 * (beta - ee);
     f.PoY = -16 * io; f.PeY = -16 * ie; f.PeoY = -16 * eo; f.PeeY = -16 * ee;
-    // range: every value of the (padded) DP stays inside the unsigned 16-bit window around the bias
+    // range: every reachable value of the (padded) DP must fit the unsigned 16-bit window.
+    // Lowest real value: a leading end gap to the diagonal, then mismatches (0 in the transformed
+    // space), plus one gap opening for the Ix / Iy states; highest: all matches.  Dead slots idle at
+    // F16_NEG minus at most one penalty.  The bias is placed just above the dead band.
     const long long R = 32LL * H, C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
     const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
-    if (pen_o > 1500 || pen_e > 1500) return false;   // dead slots idle at F16_NEG - one penalty: must stay >= 0
-    const long long lower = 2 * pen_o + (R + C) * pen_e, upper = (long long)f.D16 * std::min(R, C);
-    if (0x8000LL - lower < 0x0800LL + 2 * 2048 || 0x8000LL + upper > 65000) return false;
+    if (pen_o > 1500 || pen_e > 1500) return false;
+    const long long lower = std::max<long long>(f.PeoX + R * f.PeeX, f.PeoY + C * f.PeeY) + pen_o + pen_e;
+    const long long upper = (long long)f.D16 * std::min<long long>(max_rows, C);
+    const long long floor_v = 0x0800 + 256;                      // top of the dead band (F16_NEG + tags + slack)
+    const long long bias = (floor_v + lower + 15) / 16 * 16;
+    if (bias + upper > 65535 - 512) return false;
+    f.bias = (int32_t)bias;
     *out = f; *H_out = H;
     *mode_out = bottom ? 1 : 0;
     return true;
