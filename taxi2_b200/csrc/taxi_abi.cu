@@ -563,35 +563,56 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
     c->cells += cells_rect(c->set[0], yset(c), x0, nx, y0, ny);
 
-    // Mixed lengths (BASELINE config C5): the packed kernel only takes rows of up to one stripe.
-    // If only some rows are too long, split the rectangle's rows into two lists -- short rows
-    // go through the packed kernel, long rows through the general one -- instead of letting a
-    // few long sequences pull the whole launch onto the slower kernel.
-    Fast16 f16{};
-    int H = 0, mode = 0;
-    if (!fast16_eligible(c, mr, mc, &f16, &H, &mode)) {
+    // Mixed lengths (BASELINE config C5).  The packed kernel keeps 32*H row slots per pair, so a
+    // rectangle whose rows differ a lot in length wastes slots -- and rows longer than one stripe
+    // cannot use it at all.  Rows are therefore grouped by the smallest kernel geometry that holds
+    // them (packed H = 8..32, else the general kernel) and every group gets its own launch over a
+    // row list; results still land in the rectangle's row-major positions.
+    {
         const SeqSet& X = c->set[0];
-        const int limit = 32 * 32 - 1;
-        std::vector<int32_t> rows_short, rows_long;
-        int mr_short = 0, mr_long = 0;
+        const bool bottom = (c->raw_scores[3] == c->raw_scores[5]) && !c->force_top;
+        constexpr int K = (int)(sizeof(kDispatch16) / sizeof(kDispatch16[0]));
+        std::vector<int32_t> rows[K + 1];
+        int maxlen[K + 1] = {0};
         for (int32_t i = x0; i < x0 + nx; ++i) {
             const int len = (int)(X.off[i + 1] - X.off[i]);
-            if (len <= limit) { rows_short.push_back(i); mr_short = std::max(mr_short, len); }
-            else { rows_long.push_back(i); mr_long = std::max(mr_long, len); }
+            int k = 0;
+            while (k < K && 32 * kDispatch16[k].H - (bottom ? 1 : 0) < len) ++k;
+            rows[k].push_back(i);
+            maxlen[k] = std::max(maxlen[k], len);
         }
-        if (!rows_short.empty() && !rows_long.empty() && fast16_eligible(c, mr_short, mc, &f16, &H, &mode)) {
+        // fold small groups upwards (a launch should have enough pairs to fill the GPU)
+        const long long min_pairs = 8LL * c->sms * 24;
+        for (int k = 0; k < K - 1; ++k) {
+            if (!rows[k].empty() && (long long)rows[k].size() * ny < min_pairs) {
+                rows[k + 1].insert(rows[k + 1].end(), rows[k].begin(), rows[k].end());
+                maxlen[k + 1] = std::max(maxlen[k + 1], maxlen[k]);
+                rows[k].clear();
+            }
+        }
+        int groups = 0;
+        for (int k = 0; k <= K; ++k) groups += !rows[k].empty();
+        Fast16 f16{};
+        int H = 0, mode = 0;
+        if (groups > 1 && !c->force_general && fast16_eligible(c, std::min(mr, 32 * 32 - 1), mc, &f16, &H, &mode)) {
+            std::vector<int32_t> all;
+            all.reserve((size_t)nx);
+            for (int k = 0; k <= K; ++k) all.insert(all.end(), rows[k].begin(), rows[k].end());
             CUDA_TRY(c->d_xrows.reserve((size_t)nx));
-            CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p, rows_short.data(), rows_short.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p + rows_short.size(), rows_long.data(), rows_long.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));   // the row lists are host vectors about to go out of scope
-            AlignArgs a1 = a, a2 = a;
-            a1.xrows = c->d_xrows.p; a1.npairs = (long long)rows_short.size() * ny;
-            a2.xrows = c->d_xrows.p + rows_short.size(); a2.npairs = (long long)rows_long.size() * ny;
-            if ((rc = enqueue_align(c, a1, mr_short, mc, true, true))) return rc;
-            const int k1 = c->last_kernel;
-            if ((rc = enqueue_align(c, a2, mr_long, mc, false, false))) return rc;
-            c->last_kernel = 48;   // split launch: packed (k1) + general
-            (void)k1;
+            CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));   // `all` is a host vector about to go out of scope
+            size_t at = 0;
+            bool first = true;
+            for (int k = 0; k <= K; ++k) {
+                if (rows[k].empty()) continue;
+                AlignArgs ak = a;
+                ak.xrows = c->d_xrows.p + at;
+                ak.npairs = (long long)rows[k].size() * ny;
+                if ((rc = enqueue_align(c, ak, maxlen[k], mc, first, first))) return rc;
+                at += rows[k].size();
+                first = false;
+            }
+            c->last_kernel = 48;   // several launches: rows split by length
             return TAXI_OK;
         }
     }
