@@ -122,6 +122,38 @@ int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, 
                             int32_t* out_index_host, double* out_value_host);
 
 /*
+ * Host-side batch formatter and subset aggregator (no GPU involved; taxi2_b200/csrc/host_format.cpp)
+ * for the result files of the tasks: replaces the per-value `str.format` + `.send` writers
+ * (distances.py:95-186, 244-279; versus_all.py:278-350) and the per-pair dict aggregation
+ * (versus_all.py:57-95, 623-645).  All functions APPEND rows to `path` (the caller writes the
+ * header line); `metrics` is the block-local [nx][ny][4] fp64 array of an align/count call,
+ * `undefined` an optional [nx][ny] mask forcing the missing marker (versus_all.py:549-552),
+ * `float_format` a printf format equivalent to the Python spec ("{:.4f}" -> "%.4f").
+ *
+ * taxi_format_pairs: one row per pair, fields joined by tabs in the order given by `segments`:
+ * 0..3 = x string table k, 4..7 = y string table k-4 (tables = concatenated bytes + offsets, x
+ * tables are indexed by x0 + row), 8 = the selected metric columns, 9 = the comparison type derived
+ * from the genus / species subset ids (NULL = no partition; labels in ComparisonType order).
+ */
+int taxi_format_pairs(const char* path, const int32_t* segments, int32_t nsegments,
+                      const char* const* xbytes, const int64_t* const* xoff,
+                      const char* const* ybytes, const int64_t* const* yoff,
+                      int32_t x0, int32_t nx, int32_t ny,
+                      const double* metrics, const uint8_t* undefined,
+                      const int32_t* columns, int32_t ncolumns, double scale,
+                      const char* float_format, const char* missing,
+                      const int32_t* xgenus, const int32_t* xspecies, const int32_t* ygenus, const int32_t* yspecies,
+                      const char* const* type_labels, int32_t threads);
+/* DistanceHandler.Matrix rows: x id, then one value of metric `column` per y. */
+int taxi_format_matrix(const char* path, const char* xid_bytes, const int64_t* xid_off, int32_t x0, int32_t nx, int32_t ny,
+                       const double* metrics, const uint8_t* undefined, int32_t column, double scale,
+                       const char* float_format, const char* missing, int32_t threads);
+/* SimpleAggregator state (sum, min, max, n, first-seen order) per (subset_x, subset_y), row-major order. */
+int taxi_aggregate_subsets(const double* metrics, const uint8_t* undefined, int32_t x0, int32_t nx, int32_t ny,
+                           int32_t column, double scale, const int32_t* xsubset, const int32_t* ysubset, int32_t nsub,
+                           double* sum, double* vmin, double* vmax, int64_t* count, int64_t* first_seen, int64_t* next_order);
+
+/*
  * Page-locked host buffers for the host-facing calls above: results land in them with an
  * asynchronous DMA instead of a staged pageable copy.  Plain malloc'ed buffers work too.
  */

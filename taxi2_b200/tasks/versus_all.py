@@ -15,6 +15,7 @@ from typing import Callable, Iterator, NamedTuple
 
 import numpy as np
 
+from .. import fastwrite
 from ..align import Scores
 from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..handlers import FileHandler
@@ -55,10 +56,23 @@ class DistanceStatistics(NamedTuple):
     count: int
 
 
+class _FixedStatistics:
+    """Aggregate that was computed elsewhere (native aggregator)."""
+
+    def __init__(self, mn, mx, mean, n):
+        self.stats = (mn, mx, mean, n)
+
+    def calculate(self):
+        return self.stats
+
+
 class DistanceAggregator:
     def __init__(self, metric: DistanceMetric):
         self.metric = metric
         self.aggs: dict = {}
+
+    def set(self, idx, idy, mn, mx, mean, n) -> None:
+        self.aggs[(idx, idy)] = _FixedStatistics(mn, mx, mean, n)
 
     def add(self, idx, idy, d) -> None:
         agg = self.aggs.get((idx, idy))
@@ -92,6 +106,7 @@ class VersusAll:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.native_writers: bool = True   # batch formatter for plain float formats (same bytes as the handlers)
 
         self.input = AttrDict()
         self.input.sequences: Sequences = None
@@ -162,25 +177,37 @@ class VersusAll:
 
         total = len(metrics) * n * n
         done, last_time = 0, perf_counter()
+        fmtc = fastwrite.printf_format(fmt) if self.native_writers else None
+        native = NativeBlockWriter(self, sequences, metrics, columns, scale, fmtc, missing, linear_file, matrix_files, summary,
+                                   agg_genera, agg_species) if fmtc else None
+        same_key = duplicate_groups(sequences)
         try:
             for block in iter_pair_blocks(engine, sequences, None, p.pairs.align, pairs_file is not None, p.pairs.scores):
+                undefined = self._undefined_mask(engine, block, sequences, same_key, p.pairs.align)
+                if pairs_file is not None:
+                    for bx in range(block.nx):
+                        x = sequences[block.x0 + bx]
+                        for j, y in enumerate(sequences):
+                            ax, ay = block.aligned[bx * n + j]
+                            pairs_file.write(SequencePair(Sequence(x.id, ax, x.extras), Sequence(y.id, ay, y.extras)))
+                if native is not None:
+                    native.write_block(block, undefined)
+                    done += len(metrics) * block.nx * n
+                    now = perf_counter()
+                    if now - last_time >= self.progress_interval:
+                        self.progress_handler("distance.x.id", done, total)
+                        last_time = now
+                    continue
                 for bx in range(block.nx):
                     x = sequences[block.x0 + bx]
                     for j in range(n):
                         y = sequences[j]
-                        if block.aligned is not None:
-                            ax, ay = block.aligned[bx * n + j]
-                            pair = SequencePair(Sequence(x.id, ax, x.extras), Sequence(y.id, ay, y.extras))
-                            pairs_file.write(pair)
-                        else:
-                            pair = SequencePair(x, y)
-                        undefined = self._same_record(engine, block.x0 + bx, j, x, y, pair, p.pairs.align, block.aligned is not None)
                         row = []
                         for metric, col in zip(metrics, columns):
-                            d = None if undefined else number_or_none(block.metrics[bx, j, col])
+                            d = None if undefined[bx, j] else number_or_none(block.metrics[bx, j, col])
                             if d is not None:
                                 d *= scale
-                            row.append(Distance(metric, pair.x, pair.y, d))
+                            row.append(Distance(metric, x, y, d))
                         for k, distance in enumerate(row):
                             if linear_file:
                                 linear_file.write(distance)
@@ -199,6 +226,8 @@ class VersusAll:
             for w in writers:
                 w.close()
             summary.close()
+        if native is not None:
+            native.finish()
         if agg_genera:
             agg_genera.write(self.paths.subsets / "genera", p.format)
         if agg_species:
@@ -206,18 +235,142 @@ class VersusAll:
         return Results(self.work_dir, perf_counter() - ts)
 
     @staticmethod
-    def _same_record(engine, i: int, j: int, x: Sequence, y: Sequence, pair: SequencePair, aligned: bool, have_strings: bool) -> bool:
+    def _undefined_mask(engine, block, sequences, same_key, aligned: bool) -> np.ndarray:
         """versus_all.py:549-552: distances are None when the two (aligned) records compare equal as
-        tuples.  Equal aligned strings imply equal raw strings, so only candidates with identical
-        id / sequence / extras need the alignment itself (one extra single-pair launch each)."""
-        if x.id != y.id or x.seq != y.seq or x.extras != y.extras:
-            return False
+        tuples.  Equal aligned strings imply equal raw strings, so only pairs of records with
+        identical id / sequence / extras are candidates; when aligned they are settled by the
+        alignment itself (strings of this block if they were produced, else one small extra launch)."""
+        n = len(sequences)
+        mask = np.zeros((block.nx, n), dtype=np.uint8)
+        cand = [(bx, j) for bx in range(block.nx) for j in same_key[block.x0 + bx]]
+        if not cand:
+            return mask
         if not aligned:
-            return True
-        if have_strings:
-            return pair.x == pair.y
-        ax, ay, _ = engine.align_strings([i], [j])   # indices into the loaded set (it serves both sides)
-        return ax[0] == ay[0]
+            for bx, j in cand:
+                mask[bx, j] = 1
+            return mask
+        if block.aligned is not None:
+            for bx, j in cand:
+                ax, ay = block.aligned[bx * n + j]
+                mask[bx, j] = ax == ay
+            return mask
+        px = np.array([block.x0 + bx for bx, _ in cand], dtype=np.int32)
+        py = np.array([j for _, j in cand], dtype=np.int32)
+        ax, ay, _ = engine.align_strings(px, py)   # indices into the loaded set (it serves both sides)
+        for k, (bx, j) in enumerate(cand):
+            mask[bx, j] = ax[k] == ay[k]
+        return mask
+
+
+def duplicate_groups(sequences) -> list[list[int]]:
+    """For every record, the indices of all records that equal it as a tuple (itself included)."""
+    groups: dict = {}
+    for k, s in enumerate(sequences):
+        groups.setdefault((s.id, s.seq, tuple(s.extras.items())), []).append(k)
+    return [groups[(s.id, s.seq, tuple(s.extras.items()))] for s in sequences]
+
+
+class NativeBlockWriter:
+    """Feeds whole result blocks to the native formatter / aggregator (fastwrite) instead of
+    sending every value through the Python handlers.  Same files, same bytes."""
+
+    def __init__(self, task, sequences, metrics, columns, scale, fmtc, missing, linear_file, matrix_files, summary, agg_genera, agg_species):
+        self.task, self.sequences, self.metrics, self.columns = task, sequences, metrics, columns
+        self.scale, self.fmtc, self.missing = scale, fmtc, missing
+        self.n = len(sequences)
+        self.linear_path = task.paths.distances_linear if linear_file is not None else None
+        self.matrix_paths = [task.paths.distances_matricial / f"{m}.tsv" for m in metrics] if matrix_files else []
+        self.summary_path = task.paths.summary
+        self.agg = {"genera": agg_genera, "species": agg_species}
+        self.header_done = False
+        # the Python handlers stay open (they create / truncate the files) but never receive a row;
+        # they are closed before the first native append so the two never interleave
+        self.python_handles = [h for h in [linear_file, *matrix_files] if h is not None]
+        self.summary = summary
+        fill = lambda values: [missing if v is None else v for v in values]  # noqa: E731
+        ids = [s.id for s in sequences]
+        self.t_id = fastwrite.StringTable(ids)
+        self.t_rec = fastwrite.StringTable(["\t".join([s.id, *fill(s.extras.values())]) for s in sequences])
+        self.has_extras = bool(sequences) and bool(sequences[0].extras)
+        self.t_extras = fastwrite.StringTable(["\t".join(fill(s.extras.values())) for s in sequences])
+        genera, species = task.input.genera, task.input.species
+        taxon = lambda part, s: ((part.get(s.id, None) if part else None) or "-")  # noqa: E731
+        self.t_taxon = fastwrite.StringTable([taxon(genera, s) + "\t" + taxon(species, s) for s in sequences])
+        self.ids = {}
+        self.states = {}
+        for name, part in (("genera", genera), ("species", species)):
+            if not part:
+                self.ids[name] = None
+                continue
+            names: dict = {}
+            raw = [part.get(s.id, None) for s in sequences]
+            for v in raw:
+                if v is not None:
+                    names.setdefault(v, len(names))
+            comp = np.array([names[v] if v is not None else -1 for v in raw], dtype=np.int32)
+            agg = np.array([names[v] if v is not None else len(names) for v in raw], dtype=np.int32)
+            self.ids[name] = (comp, agg, [*names, None])
+            self.states[name] = [fastwrite.NativeSubsetState(len(names) + 1) for _ in metrics]
+
+    def _headers(self):
+        for h in self.python_handles:
+            h.close()
+        self.summary.close()
+        if not self.n:
+            return
+        first = self.sequences[0]
+        labels = [str(m) for m in self.metrics]
+        if self.linear_path is not None:
+            row = ("seqid (query)", *(k + " (query)" for k in first.extras), "seqid (reference)",
+                   *(k + " (reference)" for k in first.extras), *labels)
+            self.linear_path.write_text("\t".join(row) + "\n")
+        for path in self.matrix_paths:
+            path.write_text("\t".join(("", *(s.id for s in self.sequences))) + "\n")
+        tx, ty = " (query 1)", " (query 2)"
+        row = ("seqid" + tx, "seqid" + ty, *labels, *(k + tx for k in first.extras), *(k + ty for k in first.extras),
+               "genus" + tx, "species" + tx, "genus" + ty, "species" + ty, "comparison_type")
+        self.summary_path.write_text("\t".join(row) + "\n")
+
+    def write_block(self, block, undefined) -> None:
+        if not self.header_done:
+            self._headers()
+            self.header_done = True
+        fw = fastwrite
+        n, m = self.n, block.metrics
+        if self.linear_path is not None:
+            fw.format_pairs(self.linear_path, [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES], [self.t_rec], [self.t_rec], block.x0, block.nx, n,
+                            m, undefined, self.columns, self.scale, self.fmtc, self.missing)
+        for path, col in zip(self.matrix_paths, self.columns):
+            fw.format_matrix(path, self.t_id, block.x0, block.nx, n, m, undefined, col, self.scale, self.fmtc, self.missing)
+        seg = [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES]
+        if self.has_extras:
+            seg += [fw.SEG_X[1], fw.SEG_Y[1]]
+        seg += [fw.SEG_X[2], fw.SEG_Y[2], fw.SEG_COMPARISON]
+        g, s = self.ids["genera"], self.ids["species"]
+        fw.format_pairs(self.summary_path, seg, [self.t_id, self.t_extras, self.t_taxon], [self.t_id, self.t_extras, self.t_taxon],
+                        block.x0, block.nx, n, m, undefined, self.columns, self.scale, self.fmtc, self.missing,
+                        xgenus=g[0] if g else None, xspecies=s[0] if s else None, ygenus=g[0] if g else None, yspecies=s[0] if s else None)
+        for name in ("genera", "species"):
+            if self.ids[name] is None:
+                continue
+            agg_ids = self.ids[name][1]
+            for state, col in zip(self.states[name], self.columns):
+                state.add_block(m, undefined, block.x0, block.nx, n, col, self.scale, agg_ids, agg_ids)
+
+    def finish(self) -> None:
+        if not self.header_done:   # no sequences at all: the handlers produced the (empty) files
+            for h in self.python_handles:
+                h.close()
+            self.summary.close()
+        for name in ("genera", "species"):
+            agg = self.agg[name]
+            if agg is None:
+                continue
+            subset_names = self.ids[name][2]
+            for metric, state in zip(self.metrics, self.states[name]):
+                target = agg.aggregators[str(metric)]
+                for (sx, sy), (mn, mx, mean, cnt) in state.items():
+                    target.set(subset_names[sx], subset_names[sy], mn, mx, mean, cnt)
 
 
 class SubsetAggregation:

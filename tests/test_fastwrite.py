@@ -1,0 +1,120 @@
+"""Native batch formatter / aggregator (host C++, no GPU) against the Python handlers it replaces:
+same bytes in the files, same fp64 aggregates, for several float formats incl. NaN / masked values."""
+from __future__ import annotations
+
+from math import inf, isnan
+
+import numpy as np
+import pytest
+
+from taxi2_b200 import fastwrite as fw
+from taxi2_b200.distances import Distance, DistanceHandler, DistanceMetric
+from taxi2_b200.sequences import Sequence
+
+METRICS = [DistanceMetric.Uncorrected(), DistanceMetric.UncorrectedWithGaps(), DistanceMetric.JukesCantor(), DistanceMetric.Kimura2P()]
+
+
+def make_block(nx, ny, seed=0):
+    rng = np.random.default_rng(seed)
+    m = rng.random((nx, ny, 4))
+    m[rng.random((nx, ny, 4)) < 0.1] = np.nan
+    # values that sit exactly on decimal rounding ties in binary (0.03125 -> "0.0312", 0.5, 0.125 ...)
+    m[0, 0] = [0.03125, 0.5, 0.125, 0.09375]
+    m[0, 1 % ny] = [0.0, 1.0, 2.5, 1e-7]
+    undefined = (rng.random((nx, ny)) < 0.1).astype(np.uint8)
+    undefined[0, 0] = undefined[0, 1 % ny] = 0
+    xs = [Sequence(f"x{i}", None, {"voucher": f"v{i}", "organism": None if i % 3 == 0 else f"Genus{i % 2} sp{i % 5}"}) for i in range(nx)]
+    ys = [Sequence(f"y{j}", None, {"voucher": f"w{j}", "organism": f"Genus{j % 2} sp{j % 4}"}) for j in range(ny)]
+    return m, undefined, xs, ys
+
+
+def value(m, undefined, i, j, c, scale):
+    v = m[i, j, c]
+    return None if (undefined[i, j] or isnan(v)) else v * scale
+
+
+@pytest.mark.parametrize("spec,scale,missing", [("{:.4f}", 1.0, "NA"), ("{:f}", 100.0, "nan"), ("{:.2e}", 1.0, "NA"), ("{:.0f}", 100.0, "-")])
+def test_linear_and_matrix_rows_match_the_python_handlers(tmp_path, spec, scale, missing):
+    nx, ny = 7, 5
+    m, undefined, xs, ys = make_block(nx, ny)
+    fmt = fw.printf_format(spec)
+    cols = [0, 1, 2, 3]
+    # Python handlers (the reference's writer logic)
+    want_linear, want_matrix = tmp_path / "want.linear", tmp_path / "want.matrix"
+    with DistanceHandler.Linear.WithExtras(want_linear, "w", missing=missing, formatter=spec) as lin, \
+            DistanceHandler.Matrix(want_matrix, "w", missing=missing, formatter=spec) as mat:
+        for i in range(nx):
+            for j in range(ny):
+                for c, metric in zip(cols, METRICS):
+                    d = Distance(metric, xs[i], ys[j], value(m, undefined, i, j, c, scale))
+                    lin.write(d)
+                    if c == 2:
+                        mat.write(d)
+    # native: header in Python, rows from the library, in two blocks with a row offset
+    got_linear, got_matrix = tmp_path / "got.linear", tmp_path / "got.matrix"
+    fill = lambda s: [missing if v is None else v for v in s.extras.values()]  # noqa: E731
+    xt = fw.StringTable(["\t".join([s.id, *fill(s)]) for s in xs])
+    yt = fw.StringTable(["\t".join([s.id, *fill(s)]) for s in ys])
+    xid = fw.StringTable([s.id for s in xs])
+    got_linear.write_text("\t".join(["seqid (query)", "voucher (query)", "organism (query)", "seqid (reference)", "voucher (reference)",
+                                     "organism (reference)", "p", "p-gaps", "jc", "k2p"]) + "\n")
+    got_matrix.write_text("\t".join(["", *(s.id for s in ys)]) + "\n")
+    for x0, rows in ((0, 3), (3, 4)):
+        blk, und = m[x0:x0 + rows], np.ascontiguousarray(undefined[x0:x0 + rows])
+        fw.format_pairs(got_linear, [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES], [xt], [yt], x0, rows, ny, blk, und, cols, scale, fmt, missing, threads=3)
+        fw.format_matrix(got_matrix, xid, x0, rows, ny, blk, und, 2, scale, fmt, missing, threads=2)
+    assert got_linear.read_bytes() == want_linear.read_bytes()
+    assert got_matrix.read_bytes() == want_matrix.read_bytes()
+
+
+def test_unsupported_format_specs_fall_back():
+    assert fw.printf_format("{:.4f}") == "%.4f" and fw.printf_format("{:f}") == "%f" and fw.printf_format("{:.3e}") == "%.3e"
+    assert fw.printf_format("{:>10.4f}") is None and fw.printf_format("{:.2%}") is None and fw.printf_format("{}") is None
+
+
+def test_subset_aggregation_matches_the_reference_order_and_sums():
+    nx, ny = 9, 8
+    m, undefined, xs, ys = make_block(nx, ny, seed=3)
+    names = {}
+    ident = lambda name: names.setdefault(name, len(names))  # noqa: E731
+    xsub = np.array([ident(s.extras["organism"]) for s in xs], dtype=np.int32)
+    ysub = np.array([ident(s.extras["organism"]) for s in ys], dtype=np.int32)
+    state = fw.NativeSubsetState(len(names))
+    for x0, rows in ((0, 4), (4, 5)):
+        state.add_block(m[x0:x0 + rows], np.ascontiguousarray(undefined[x0:x0 + rows]), x0, rows, ny, 1, 100.0, xsub, ysub)
+    want = {}
+    for i in range(nx):
+        for j in range(ny):
+            a = want.setdefault((int(xsub[i]), int(ysub[j])), [0.0, inf, 0.0, 0])
+            v = value(m, undefined, i, j, 1, 100.0)
+            if v is not None:
+                a[0] += v; a[1] = min(a[1], v); a[2] = max(a[2], v); a[3] += 1
+    got = list(state.items())
+    assert [k for k, _ in got] == list(want)                       # insertion order of the reference's dict
+    for (key, (mn, mx, mean, n)) in got:
+        s = want[key]
+        assert n == s[3]
+        if n:
+            assert (mn, mx, mean) == (s[1], s[2], s[0] / s[3])      # bit-identical fp64
+
+
+def test_comparison_type_column(tmp_path):
+    nx, ny = 4, 4
+    m, undefined, xs, ys = make_block(nx, ny, seed=5)
+    genus = np.array([0, 0, 1, -1], dtype=np.int32)
+    species = np.array([0, 1, 2, -1], dtype=np.int32)
+    xid = fw.StringTable([s.id for s in xs])
+    yid = fw.StringTable([s.id for s in ys])
+    for g, s in ((genus, species), (None, species), (genus, None), (None, None)):
+        out = tmp_path / "types.tsv"
+        out.write_text("")
+        fw.format_pairs(out, [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_COMPARISON], [xid], [yid], 0, nx, ny, m, None, [0], 1.0, "%.4f", "NA",
+                        xgenus=g, xspecies=s, ygenus=g, yspecies=s, threads=1)
+        rows = [line.split("\t") for line in out.read_text().splitlines()]
+        for r, (i, j) in zip(rows, ((i, j) for i in range(nx) for j in range(ny))):
+            sg = None if g is None else bool(g[i] == g[j])
+            ss = None if s is None else bool(s[i] == s[j])
+            want = {(None, None): "no info", (None, True): "intra-species", (None, False): "inter-species",
+                    (False, None): "inter-genus", (False, True): "inter-genus", (False, False): "inter-genus",
+                    (True, None): "intra-genus", (True, True): "intra-species", (True, False): "inter-species"}[(sg, ss)]
+            assert r == [xs[i].id, ys[j].id, want]

@@ -37,8 +37,9 @@ def assert_same_tree(got: Path, want: Path):
         assert (got / rel).read_bytes() == (want / rel).read_bytes(), rel
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("align,write,multiply", [(True, True, False), (True, False, True), (False, False, False)])
-def test_versus_all_outputs(tmp_path, align, write, multiply):
+def test_versus_all_outputs(tmp_path, align, write, multiply, native):
     seqs, species, genera = load("Taxi2test1_10.tab")
     # a duplicated record and a pair of different records with equal sequences exercise the x != y quirk
     records = list(seqs)
@@ -51,6 +52,7 @@ def test_versus_all_outputs(tmp_path, align, write, multiply):
     task.input.species, task.input.genera = species, genera
     task.params.pairs.align, task.params.pairs.write = align, write
     task.params.format.percentage_multiply = multiply
+    task.native_writers = native   # batch formatter vs the per-value Python handlers: same bytes
     results = task.start()
     assert results.output_directory == task.work_dir and results.seconds_taken > 0
     want = tmp_path / "want"
@@ -61,15 +63,28 @@ def test_versus_all_outputs(tmp_path, align, write, multiply):
     assert_same_tree(task.work_dir, want)
 
 
-def test_versus_all_without_partitions_and_metric_subset(tmp_path):
+@pytest.mark.parametrize("fmt", ["{:.4f}", "{:.2e}", "{:>9.3f}"])
+def test_versus_all_without_partitions_and_metric_subset(tmp_path, fmt):
     seqs, _, _ = load("Taxi2test1_10.tab")
     task = VersusAll()
     task.work_dir = tmp_path / "got"
     task.progress_handler = SILENT
     task.input.sequences = seqs
     task.params.distances.metrics = [DistanceMetric.Kimura2P(), DistanceMetric.Uncorrected()]
+    task.params.format.float = fmt      # the last one is not a plain spec: Python handlers take over
     task.start()
-    ref_pipeline.versus_all(list(seqs), tmp_path / "want", metrics=[DistanceMetric.Kimura2P(), DistanceMetric.Uncorrected()])
+    ref_pipeline.versus_all(list(seqs), tmp_path / "want", metrics=[DistanceMetric.Kimura2P(), DistanceMetric.Uncorrected()], fmt=fmt)
+    assert_same_tree(task.work_dir, tmp_path / "want")
+
+
+def test_versus_all_sequences_without_extras(tmp_path):
+    records = [Sequence(f"s{k}", seq) for k, seq in enumerate(["ACGTACGTAC", "ACGTTCGTAC", "ACG-ACGNAC", "TTGTACGAAC"])]
+    task = VersusAll()
+    task.work_dir = tmp_path / "got"
+    task.progress_handler = SILENT
+    task.input.sequences = Sequences(records)
+    task.start()
+    ref_pipeline.versus_all(records, tmp_path / "want")
     assert_same_tree(task.work_dir, tmp_path / "want")
 
 
