@@ -13,6 +13,7 @@ from pathlib import Path
 from time import perf_counter
 from typing import Callable
 
+from .. import fastwrite
 from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, Sequences
@@ -27,6 +28,7 @@ class VersusReference:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.native_writers: bool = True   # batch formatter for plain float formats (same bytes as the handlers)
 
         self.input = AttrDict()
         self.input.data: Sequences = None
@@ -92,9 +94,39 @@ class VersusReference:
         total = len(data) * nref
         state = dict(done=0, last=perf_counter())
 
+        fmtc = fastwrite.printf_format(fmt) if self.native_writers else None
+        fill = lambda values: [missing if v is None else v for v in values]  # noqa: E731
+        if fmtc:
+            t_x = fastwrite.StringTable(["\t".join([s.id, *fill(s.extras.values())]) for s in data])
+            t_y = fastwrite.StringTable(["\t".join([s.id, *fill(s.extras.values())]) for s in reference])
+            t_xid = fastwrite.StringTable([s.id for s in data])
+        native_started = False
+
+        def native_block(block):
+            """Append the block's rows of the linear / matrix files through the batch formatter."""
+            nonlocal native_started
+            if not native_started:
+                native_started = True
+                for handle, path, header in (
+                        (linear_file, self.paths.distances_linear,
+                         ("seqid (query)", *(k + " (query)" for k in data[0].extras), "seqid (reference)",
+                          *(k + " (reference)" for k in reference[0].extras), str(main))),
+                        (matrix_file, self.paths.distances_matricial, ("", *(s.id for s in reference)))):
+                    if handle is not None:
+                        handle.close()
+                        path.write_text("\t".join(header) + "\n")
+            if linear_file is not None:
+                fastwrite.format_pairs(self.paths.distances_linear, [fastwrite.SEG_X[0], fastwrite.SEG_Y[0], fastwrite.SEG_SCORES],
+                                       [t_x], [t_y], block.x0, block.nx, nref, block.metrics, None, [main_col], scale, fmtc, missing)
+            if matrix_file is not None:
+                fastwrite.format_matrix(self.paths.distances_matricial, t_xid, block.x0, block.nx, nref, block.metrics, None, main_col,
+                                        scale, fmtc, missing)
+
         def main_distances():
             """(Distance of the main metric, all four raw metrics of the pair) in product order."""
             for block in iter_pair_blocks(engine, data, reference, p.pairs.align, pairs_file is not None, p.pairs.scores):
+                if fmtc and data and reference:
+                    native_block(block)
                 for bx in range(block.nx):
                     x = data[block.x0 + bx]
                     for j, y in enumerate(reference):
@@ -113,10 +145,11 @@ class VersusReference:
                         if d is not None:
                             d *= scale
                         distance = Distance(main, pair.x, pair.y, d)
-                        if linear_file:
-                            linear_file.write(distance)
-                        if matrix_file:
-                            matrix_file.write(distance)
+                        if not fmtc:
+                            if linear_file:
+                                linear_file.write(distance)
+                            if matrix_file:
+                                matrix_file.write(distance)
                         yield distance, block.metrics[bx, j]
             self.progress_handler("Finalizing...", total, total)
 

@@ -88,8 +88,9 @@ def test_versus_all_sequences_without_extras(tmp_path):
     assert_same_tree(task.work_dir, tmp_path / "want")
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("align,multiply,main", [(True, False, "p"), (True, True, "k2p"), (False, False, "p-gaps")])
-def test_versus_reference_outputs(tmp_path, align, multiply, main):
+def test_versus_reference_outputs(tmp_path, align, multiply, main, native):
     seqs, _, _ = load("Taxi2test1_50.tab")
     records = list(seqs)
     data, reference = records[:12], records[12:40]
@@ -100,6 +101,7 @@ def test_versus_reference_outputs(tmp_path, align, multiply, main):
     task.params.pairs.align = align
     task.params.distances.metric = DistanceMetric.fromLabel(main)
     task.params.format.percentage_multiply = multiply
+    task.native_writers = native
     task.start()
     ref_pipeline.versus_reference(data, reference, tmp_path / "want", align=align, metric=DistanceMetric.fromLabel(main), multiply=multiply)
     assert_same_tree(task.work_dir, tmp_path / "want")
