@@ -24,10 +24,12 @@ struct ScoreSet {
 
 // constants of the packed 16-bit fast path (gotoh_pair16.cuh), transformed score space, x16
 struct Fast16 {
-    int32_t D16;                       // (match - beta) * 16, <= 255 (the mismatch increment is 0)
-    int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties: internal open/extend, end open/extend
-    int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties
-    int32_t beta;                      // min(match, mismatch), unscaled
+    int32_t D16;                       // (match - mismatch) * 16 <= 127: penalty of a mismatching column (a match costs 0)
+    uint32_t tlo, thi;                 // PRMT table indexed by the XOR of two symbol codes: byte 0 = 0, bytes 1..7 = D16
+    int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties 16*(match - g): internal open/extend, end open/extend
+    int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties -16*g
+    int32_t beta;                      // row potential of the transformed space (= match), unscaled
+    int32_t neg;                       // "minus infinity" of the dead slots (multiple of 16, above every penalty)
     int32_t bias;                      // value representing transformed score 0 (multiple of 16), placed by the host so that
                                        // every reachable value of the padded DP fits the unsigned 16-bit window
 };

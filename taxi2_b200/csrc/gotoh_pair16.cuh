@@ -6,10 +6,12 @@
 //
 //  1. 16-bit cells.  Each 32-bit register holds the same DP cell of two different pairs (low
 //     half = pair A, high half = pair B), so every VIMNMX3/VIADDMNMX (.U16x2) advances two
-//     cells.  Values are kept unsigned around a bias of 0x8000 and in the transformed score
-//     space S' = S - beta*i (beta = min(match, mismatch)), which makes every diagonal increment
-//     non-negative and every gap step a non-negative penalty; plain 32-bit IADDs then never
-//     carry between the halves.
+//     cells.  Values are kept unsigned below a bias near the top of the 16-bit range, in the
+//     transformed score space S' = S - match*i: a matching column costs 0, a mismatch
+//     match-mismatch, a vertical gap step match-g, a horizontal one -g -- every step is a
+//     non-negative penalty, the value of a perfect match stays at the bias, and plain 32-bit
+//     subtractions never borrow between the halves.  Anchoring the maximum (instead of the
+//     mismatch) keeps the window at ~2*max(len) score units, so sequences up to ~1 800 bp fit.
 //  2. Restricted recurrence.  When no co-optimal path can contain a vertical gap adjacent to a
 //     horizontal one (true for TaxI2's default scores; the host proves it per score set), the
 //     Ix<->Iy transitions of Biopython's recurrence can be dropped without changing the first
@@ -25,7 +27,6 @@
 
 namespace taxi {
 
-constexpr uint32_t F16_NEG = 0x0800u;          // "minus infinity": below every reachable value
 constexpr uint32_t F16_CLEAN = 0xFFF0FFF0u;
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return (lo & 0xFFFFu) | (hi << 16); }
@@ -243,7 +244,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
         a2[r] = c0 | (c1 << 8);
         const uint32_t xb = (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;   // Ix(i,0), tagged as state Ix
         Hl[r] = pack16(xb, xb);
-        Yn[r] = pack16(F16_NEG, F16_NEG);                                        // no Ix->Iy: Iy(i,1) opens from M only
+        Yn[r] = pack16((uint32_t)f.neg, (uint32_t)f.neg);                                        // no Ix->Iy: Iy(i,1) opens from M only
         const int yo0 = (i == A.nA) ? f.PeoY : f.PoY, yo1 = (i == B.nA) ? f.PeoY : f.PoY;
         const int ye0 = (i == A.nA) ? f.PeeY : f.PeY, ye1 = (i == B.nA) ? f.PeeY : f.PeY;
         ncYM[r] = pack16((uint32_t)(5 - yo0), (uint32_t)(5 - yo1));   // M(tag 3) -> Iy candidate with bit 3 set
@@ -277,7 +278,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
                 // row 0: only Iy is alive (leading end gap); nothing can open Ix from it
                 const uint32_t y0 = (uint32_t)f.bias - f.PeoY - (uint32_t)(j - 1) * f.PeeY + 1u;
                 rH = pack16(y0, y0);
-                rX = pack16(F16_NEG, F16_NEG);
+                rX = pack16((uint32_t)f.neg, (uint32_t)f.neg);
             }
             if (active) {
                 const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : 7u;
@@ -292,9 +293,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
                 uint32_t tprev = 0;
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
-                    const uint32_t sel = lop3_xor_or(a2[r], b2, 0x7070u);
-                    const uint32_t sub = prmt_raw((uint32_t)f.D16, 0u, sel);   // (D16 or 0) per half
-                    const uint32_t Mr = Hd + sub;
+                    const uint32_t sel = lop3_xor_or(a2[r], b2, 0x8080u);
+                    const uint32_t sub = prmt_raw(f.tlo, f.thi, sel);   // mismatch penalty (0 or D16) per half
+                    const uint32_t Mr = Hd - sub;
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);                   // 4-bit trace code per half (+ score bits above)
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
@@ -359,11 +360,11 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     const int nBmax = max(A.nB, B.nB);
     const int nsteps = nBmax + (31 - l0);
     const bool live = lane >= l0;
-    const uint32_t NEG2 = pack16(F16_NEG, F16_NEG);
+    const uint32_t NEG2 = pack16((uint32_t)f.neg, (uint32_t)f.neg);
 
     auto col0_H = [&](int i) -> uint32_t {   // H(i, 0): Ix border for i >= 1, M(0,0) for i == 0, dead above
         if (i >= 1) return (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;
-        return i == 0 ? (uint32_t)f.bias + 3u : F16_NEG;
+        return i == 0 ? (uint32_t)f.bias + 3u : (uint32_t)f.neg;
     };
 
     uint32_t a2[H], Hl[H], Yn[H];
@@ -377,7 +378,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
         // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
         const uint32_t y0 = (uint32_t)f.bias - f.PeoY + 8u;
-        Yn[r] = pack16(iA == 0 ? y0 : F16_NEG, iB == 0 ? y0 : F16_NEG);
+        Yn[r] = pack16(iA == 0 ? y0 : (uint32_t)f.neg, iB == 0 ? y0 : (uint32_t)f.neg);
     }
     const int itA = lane * H - offA, itB = lane * H - offB;   // row above my top slot
     uint32_t Hd_saved = pack16(col0_H(itA), col0_H(itB));
@@ -415,7 +416,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
             fetch_b(j + 1, nb0, nb1);
             if (active) {
                 const uint32_t b2 = b0 | (b1 << 8);
-                auto sub_of = [&](int r) -> uint32_t { return prmt_raw((uint32_t)f.D16, 0u, lop3_xor_or(a2[r], b2, 0x7070u)); };
+                auto sub_of = [&](int r) -> uint32_t { return prmt_raw(f.tlo, f.thi, lop3_xor_or(a2[r], b2, 0x8080u)); };   // mismatch penalty per half
                 uint32_t ncXM = ncXMi, cXX = cXXi;
                 if (j == A.nB || j == B.nB) {   // a vertical gap in a pair's last column is an end gap
                     const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
@@ -426,11 +427,11 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 uint32_t Xin = rX;
                 uint32_t tw[WORDS];
                 uint32_t tprev = 0;
-                uint32_t Mr = Hd_saved + sub_of(0);
+                uint32_t Mr = Hd_saved - sub_of(0);
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     uint32_t Mr_next = 0;
-                    if (r + 1 < H) Mr_next = Hl[r] + sub_of(r + 1);   // needs H(i, j-1) before it is overwritten
+                    if (r + 1 < H) Mr_next = Hl[r] - sub_of(r + 1);   // needs H(i, j-1) before it is overwritten
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);

@@ -191,23 +191,23 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     const int32_t* s = c->raw_scores;
     const int match = s[0], mm = s[1], io = s[2], ie = s[3], eo = s[4], ee = s[5];
     if (io == ie && eo == ee) return false;                 // Needleman-Wunsch order: general kernel
-    if (match < mm) return false;
-    const int beta = mm, D = match - beta;
-    if (D * 16 > 255) return false;
-    // every gap step must be a non-negative penalty in the transformed space S' = S - beta*i
+    if (match < mm || match < 0) return false;
+    const int beta = match, D = match - mm;
+    if (D * 16 > 127) return false;
+    // every gap step must be a non-negative penalty in the transformed space S' = S - match*i
     const int gaps[4] = {io, ie, eo, ee};
-    for (int g : gaps) if (g > beta || g > 0) return false;
+    for (int g : gaps) if (g > 0) return false;
     // No co-optimal path may put a vertical gap next to a horizontal one: replacing runs
     // (Iy^a Ix^b) by min(a,b) diagonals plus one gap of |a-b| must be strictly better for every
     // a, b >= 1 and every end/internal typing of the two runs (worst case: all mismatches).
     const int O[2] = {io, eo}, E[2] = {ie, ee};
     for (int tx = 0; tx < 2; ++tx)
         for (int ty = 0; ty < 2; ++ty) {
-            const int slope = E[tx] + E[ty] - beta;
+            const int slope = E[tx] + E[ty] - mm;            // mm = min(match, mismatch) here
             if (slope > 0) return false;
-            if (O[tx] + E[ty] - beta >= 0) return false;     // a > b
-            if (O[ty] + E[tx] - beta >= 0) return false;     // b > a
-            if (O[tx] + O[ty] - beta >= 0) return false;     // a == b
+            if (O[tx] + E[ty] - mm >= 0) return false;       // a > b
+            if (O[ty] + E[tx] - mm >= 0) return false;       // b > a
+            if (O[tx] + O[ty] - mm >= 0) return false;       // a == b
         }
     // geometry: single stripe; the bottom-aligned variant keeps the border row in a slot of its own
     const bool bottom = (ie == ee) && !c->force_top;
@@ -216,22 +216,27 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     if (!H) return false;
     Fast16 f;
     f.D16 = 16 * D; f.beta = beta;
-    f.PoX = 16 * (beta - io); f.PeX = 16 * (beta - ie); f.PeoX = 16 * (beta - eo); f.PeeX = 16 * (beta - ee);
+    f.tlo = (uint32_t)f.D16 * 0x01010100u; f.thi = (uint32_t)f.D16 * 0x01010101u;
+    f.PoX = 16 * (match - io); f.PeX = 16 * (match - ie); f.PeoX = 16 * (match - eo); f.PeeX = 16 * (match - ee);
     f.PoY = -16 * io; f.PeY = -16 * ie; f.PeoY = -16 * eo; f.PeeY = -16 * ee;
-    // range: every reachable value of the (padded) DP must fit the unsigned 16-bit window.
-    // Lowest real value: a leading end gap to the diagonal, then mismatches (0 in the transformed
-    // space), plus one gap opening for the Ix / Iy states; highest: all matches.  Dead slots idle at
-    // F16_NEG minus at most one penalty.  The bias is placed just above the dead band.
+    // Range.  The best transformed value is 0 (all matches), so the bias sits at the top of the
+    // window.  Lowest real value of the padded DP: a leading end gap to the diagonal followed by
+    // mismatches -- linear in (i, j), so its extreme is at a corner -- plus one gap opening for the
+    // Ix / Iy states.  Dead slots idle between `neg` and neg - (H*D16 + one penalty): each dead row
+    // is at most one mismatch below the row above it, and the top one is fed the constant `neg`.
     const long long R = 32LL * H, C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
     const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
-    if (pen_o > 1500 || pen_e > 1500) return false;
-    const long long lower = std::max<long long>(f.PeoX + R * f.PeeX, f.PeoY + C * f.PeeY) + pen_o + pen_e;
-    const long long upper = (long long)f.D16 * std::min<long long>(max_rows, C);
-    const long long floor_v = 0x0800 + 256;                      // top of the dead band (F16_NEG + tags + slack)
-    const long long bias = (floor_v + lower + 15) / 16 * 16;
-    if (bias + upper > 65535 - 512) return false;
-    f.bias = (int32_t)bias;
+    if (pen_o > 3000 || pen_e > 3000) return false;
+    const long long m = std::min(R, C);
+    const long long corner_v = f.PeoX + R * f.PeeX;                                   // (R, 0)
+    const long long corner_h = f.PeoY + C * f.PeeY;                                   // (0, C)
+    const long long corner_d = m * f.D16 + (R > C ? f.PeoX + (R - C) * f.PeeX : f.PeoY + (C - R) * f.PeeY);   // (R, C)
+    const long long lower = std::max({corner_v, corner_h, corner_d}) + pen_o + pen_e;
+    const long long neg = ((long long)H * f.D16 + pen_o + pen_e + 512 + 15) / 16 * 16;
+    const long long bias = (65535 - 256) / 16 * 16;
+    if (bias - lower < neg + 256) return false;
+    f.bias = (int32_t)bias; f.neg = (int32_t)neg;
     *out = f; *H_out = H;
     *mode_out = bottom ? 1 : 0;
     return true;
