@@ -126,9 +126,11 @@ def test_fast_path_score_sets(engine):
     rng = np.random.default_rng(16)
     xs, ys = random_pairs(rng, 300, 1, 120, sub=0.2, indel=0.06, alphabet=b"ACGTN")
     xs2, ys2 = random_pairs(rng, 300, 1, 120, sub=0.3, indel=0.1, alphabet=b"AT")
-    for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (5, -4, -10, -4, -4, -4), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2), (2, -2, -7, -3, -4, -2)]:
+    for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (4, -3, -9, -3, -3, -3), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2), (2, -2, -7, -3, -4, -2)]:
         check_pairs(engine, xs, ys, scores, expect_fast=True)
         check_pairs(engine, xs2, ys2, scores, expect_fast=True)
+    # match - mismatch > 7 does not fit the one-byte penalty table: general kernel
+    check_pairs(engine, xs[:60], ys[:60], (5, -4, -10, -4, -4, -4), expect_fast=False)
 
 
 def test_mixed_lengths_in_one_warp(engine):
