@@ -166,7 +166,8 @@ void taxi_host_free(void* p);
  * lengths; this switch exists so tests can compare the two); "force_top" = 1 keeps the packed
  * kernel on its top-aligned variant.  taxi_last_kernel() reports which kernel the last alignment
  * call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 top-aligned, 17 = gotoh_pair16
- * bottom-aligned, 48 = a rectangle whose rows were split by length between the two.
+ * bottom-aligned, 18 = gotoh_pair16 bottom-aligned in several stripes (x longer than 1023),
+ * 48 = a rectangle whose rows were grouped by length into several launches.
  */
 int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
 int taxi_last_kernel(taxi_ctx* ctx);

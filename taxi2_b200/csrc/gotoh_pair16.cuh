@@ -76,6 +76,7 @@ struct Walk {
     long long p;                          // pair index (outputs)
     int i, j, state;                      // current cell and state (0 = M, 1 = Ix, 2 = Iy)
     int half, off;                        // which 16-bit half of the arena; row -> slot offset
+    int stride;                           // steps per stripe in the arena (multi-stripe kernel)
     int same, ts, tv, gapc, pend;
     bool seen;
     int64_t wpos;                         // write cursor of the gapped strings
@@ -94,8 +95,10 @@ __device__ __forceinline__ void walk_load(const Walk& w, int lane, const uint8_t
     tb = 0; ca = 0; cb = 0;
     if (valid) {
         const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
-        const int l = slot / H, r = slot % H;
-        tb = (int)__ldcg(trace + ((size_t)(jj - 1 + l - l0) * 32 + l) * HB + 2 * r + w.half);
+        const int st = slot / (32 * H), q = slot % (32 * H);   // stripe (0 for the single-stripe kernels)
+        const int l = q / H, r = q % H;
+        const int first = (st == 0) ? l0 : 0;                  // only the first stripe starts at a later lane
+        tb = (int)__ldcg(trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half);
         ca = (int)__ldg(w.x + ii - 1);
         cb = (int)__ldg(w.y + jj - 1);
     }
@@ -176,11 +179,11 @@ __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lan
 }
 
 __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, const uint8_t* x, const uint8_t* y, int nA, int nB,
-                                           int half, int off, uint32_t fin, int beta, int bias)
+                                           int half, int off, uint32_t fin, int beta, int bias, int stride = 0)
 {
     Walk w;
     w.x = x; w.y = y; w.p = p; w.i = nA; w.j = nB; w.state = 3 - (int)(fin & 3u);
-    w.half = half; w.off = off;
+    w.half = half; w.off = off; w.stride = stride;
     w.same = w.ts = w.tv = w.gapc = w.pend = 0; w.seen = false;
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
@@ -470,6 +473,140 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 
+// Multi-stripe form of the bottom-aligned variant for x longer than 32*H - 1: the slots are cut
+// into stripes of 32*H that are swept one after the other; the bottom slot of a stripe hands its
+// Ix / H values to the top slot of the next through a small per-warp boundary buffer (two packed
+// words per column).  Kept as a separate instantiation so the single-stripe hot loop stays lean.
+template <int H>
+__device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace,
+                                                       uint32_t* bnd)
+{
+    constexpr int HB = Pair16Geom<H>::HB;
+    constexpr int WORDS = Pair16Geom<H>::WORDS;
+    constexpr int SL = 32 * H;
+    constexpr uint32_t PAD = 7u;
+    const Fast16& f = a.f16;
+    const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
+    const int nstripes = (max(A.nA, B.nA) + 1 + SL - 1) / SL;   // rows 0..nA of the longer pair
+    const int total = nstripes * SL;
+    const int offA = total - A.nA, offB = total - B.nA;
+    const int l0 = (min(offA, offB) - 1) / H;                   // < 32 by construction
+    const int nBmax = max(A.nB, B.nB);
+    const int stride = nBmax + 31;
+    const uint32_t NEG2 = pack16((uint32_t)f.neg, (uint32_t)f.neg);
+
+    auto col0_H = [&](int i) -> uint32_t {
+        if (i >= 1) return (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;
+        return i == 0 ? (uint32_t)f.bias + 3u : (uint32_t)f.neg;
+    };
+    const uint32_t ncYMi = pack16((uint32_t)(5 - f.PoY), (uint32_t)(5 - f.PoY));
+    const uint32_t cYYi = 0u - pack16((uint32_t)(f.PeY + 1), (uint32_t)(f.PeY + 1));
+    const uint32_t ncXMi = pack16((uint32_t)(1 - f.PoX), (uint32_t)(1 - f.PoX));
+    const uint32_t cXXi = 0u - pack16((uint32_t)(f.PeX + 2), (uint32_t)(f.PeX + 2));
+    uint32_t finA = 0, finB = 0;
+
+    for (int st = 0; st < nstripes; ++st) {
+        const bool last = st + 1 == nstripes;
+        const int first_lane = (st == 0) ? l0 : 0;
+        const bool live = lane >= first_lane;
+        const int nsteps = nBmax + (31 - first_lane);
+        uint32_t a2[H], Hl[H], Yn[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) {
+            const int s = st * SL + lane * H + r;
+            const int iA = s - offA + 1, iB = s - offB + 1;
+            const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
+            const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
+            a2[r] = c0 | (c1 << 8);
+            Hl[r] = pack16(col0_H(iA), col0_H(iB));
+            const uint32_t y0 = (uint32_t)f.bias - f.PeoY + 8u;
+            Yn[r] = pack16(iA == 0 ? y0 : (uint32_t)f.neg, iB == 0 ? y0 : (uint32_t)f.neg);
+        }
+        const int itA = st * SL + lane * H - offA, itB = st * SL + lane * H - offB;
+        uint32_t Hd_saved = pack16(col0_H(itA), col0_H(itB));
+        const bool end_slot = last && lane == 31;
+        const uint32_t ncYMl = end_slot ? pack16((uint32_t)(5 - f.PeoY), (uint32_t)(5 - f.PeoY)) : ncYMi;
+        const uint32_t cYYl = end_slot ? 0u - pack16((uint32_t)(f.PeeY + 1), (uint32_t)(f.PeeY + 1)) : cYYi;
+        uint32_t outX = NEG2, outH = NEG2;
+        uint8_t* tbase = trace + ((size_t)st * stride * 32 + lane) * HB;
+        const int tA = last ? A.nB - 1 + (31 - first_lane) : -2, tB = last ? B.nB - 1 + (31 - first_lane) : -2;
+        int t = 0;
+#pragma unroll 1
+        for (int seg = 0; seg < 3; ++seg) {
+            const int tend = !last ? (seg == 2 ? nsteps : 0) : ((seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps));
+            for (; t < tend; ++t) {
+                const int j = t - (lane - first_lane) + 1;
+                uint32_t rX = __shfl_up_sync(TAXI_FULL_MASK, outX, 1);
+                uint32_t rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
+                const bool active = live && j >= 1 && j <= nBmax;
+                if (lane == 0) {
+                    if (st == 0 || !active) { rX = NEG2; rH = NEG2; }
+                    else { rX = __ldcg(bnd + 2 * j); rH = __ldcg(bnd + 2 * j + 1); }
+                }
+                if (active) {
+                    const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
+                    const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
+                    const uint32_t b2 = b0 | (b1 << 8);
+                    auto sub_of = [&](int r) -> uint32_t { return prmt_raw(f.tlo, f.thi, lop3_xor_or(a2[r], b2, 0x8080u)); };
+                    uint32_t ncXM = ncXMi, cXX = cXXi;
+                    if (j == A.nB || j == B.nB) {
+                        const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
+                        const int xe0 = (j == A.nB) ? f.PeeX : f.PeX, xe1 = (j == B.nB) ? f.PeeX : f.PeX;
+                        ncXM = pack16((uint32_t)(1 - xo0), (uint32_t)(1 - xo1));
+                        cXX = 0u - pack16((uint32_t)(xe0 + 2), (uint32_t)(xe1 + 2));
+                    }
+                    uint32_t Xin = rX;
+                    uint32_t tw[WORDS];
+                    uint32_t tprev = 0;
+                    uint32_t Mr = Hd_saved - sub_of(0);
+#pragma unroll
+                    for (int r = 0; r < H; ++r) {
+                        uint32_t Mr_next = 0;
+                        if (r + 1 < H) Mr_next = Hl[r] - sub_of(r + 1);
+                        const uint32_t Yin = Yn[r];
+                        const uint32_t tc = lop3_or3(Mr, Xin, Yin);
+                        const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
+                        const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
+                        const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
+                        Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
+                        Xin = __viaddmax_u16x2(Mt, ncXM, Xt + cXX);
+                        Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt + ((r == H - 1) ? cYYl : cYYi));
+                        if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
+                        else if (r == H - 1) tw[r >> 1] = __byte_perm(tc, 0u, 0x6420);
+                        tprev = tc;
+                        Mr = Mr_next;
+                    }
+                    outX = Xin;
+                    outH = Hl[H - 1];
+                    Hd_saved = rH;
+                    uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+#pragma unroll
+                    for (int k = 0; k < HB / 16; ++k) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) w[q] = (4 * k + q < WORDS) ? tw[4 * k + q] : 0u;
+                        __stcg(dst + k, make_uint4(w[0], w[1], w[2], w[3]));
+                    }
+                    if (lane == 31 && !last) {   // hand the stripe's bottom slot to the next stripe
+                        __stcg(bnd + 2 * j, outX);
+                        __stcg(bnd + 2 * j + 1, outH);
+                    }
+                }
+            }
+            if (last && t - 1 == tA) finA = Hl[H - 1] & 0xFFFFu;
+            if (last && t - 1 == tB) finB = Hl[H - 1] >> 16;
+        }
+        __syncwarp();
+    }
+    finA = __shfl_sync(TAXI_FULL_MASK, finA, 31);
+    finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
+    __syncwarp();
+
+    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta, f.bias, stride);
+    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta, f.bias, stride);
+    traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
+}
+
 #ifndef PAIR16_WPB
 #define PAIR16_WPB 4
 #endif
@@ -478,14 +615,17 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
 #endif
 constexpr int PAIR16_WARPS_PER_BLOCK = PAIR16_WPB;
 
-// MODE 0: top-aligned rows; 1: bottom-aligned rows
+// MODE 0: top-aligned rows; 1: bottom-aligned rows; 2: bottom-aligned, several stripes (long x)
+// Three blocks of four warps (168 registers) is the measured optimum for the 21-row kernel; the
+// taller / multi-stripe instantiations need more registers and run two blocks per SM.
 template <int H, int MODE>
-__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, PAIR16_MIN_BLOCKS)
+__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, (H >= 24 || MODE == 2) ? 2 : PAIR16_MIN_BLOCKS)
 gotoh_pair16_kernel(const AlignArgs a)
 {
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * PAIR16_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     uint8_t* trace = a.trace + gw * a.trace_per_warp;
+    uint32_t* bnd = reinterpret_cast<uint32_t*>(a.bnd + gw * a.bnd_per_warp);
     const unsigned long long units = ((unsigned long long)a.npairs + 1ULL) / 2ULL;
     for (;;) {
         unsigned long long u = 0;
@@ -494,8 +634,10 @@ gotoh_pair16_kernel(const AlignArgs a)
         if (u >= units) break;
         const long long p0 = (long long)(2ULL * u);
         const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
-        if constexpr (MODE == 1) align_two_bottom<H>(a, p0, p1, lane, trace);
+        if constexpr (MODE == 2) align_two_bottom_multi<H>(a, p0, p1, lane, trace, bnd);
+        else if constexpr (MODE == 1) align_two_bottom<H>(a, p0, p1, lane, trace);
         else align_two<H>(a, p0, p1, lane, trace);
+        (void)bnd;
         __syncwarp();
     }
 }

@@ -182,6 +182,8 @@ template <int H, int MODE> void launch_pair16(const AlignArgs& a, int grid, cuda
 const Dispatch kDispatch16[] = {P16(8, 0), P16(12, 0), P16(16, 0), P16(21, 0), P16(24, 0), P16(32, 0)};
 // bottom-aligned rows (needs internal extend == end extend and one spare row slot)
 const Dispatch kDispatch16b[] = {P16(8, 1), P16(12, 1), P16(16, 1), P16(21, 1), P16(24, 1), P16(32, 1)};
+// ... in several stripes, for x longer than one stripe
+const Dispatch kDispatch16m[] = {P16(16, 2), P16(21, 2), P16(24, 2), P16(32, 2)};
 #undef P16
 
 // Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
@@ -209,11 +211,20 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
             if (O[ty] + E[tx] - mm >= 0) return false;       // b > a
             if (O[tx] + O[ty] - mm >= 0) return false;       // a == b
         }
-    // geometry: single stripe; the bottom-aligned variant keeps the border row in a slot of its own
+    // geometry: one stripe when x fits (the bottom-aligned variant keeps the border row in a slot
+    // of its own), else the multi-stripe bottom-aligned variant with the least wasted slots
     const bool bottom = (ie == ee) && !c->force_top;
-    int H = 0;
-    for (const auto& e : kDispatch16) if (32 * e.H >= max_rows + (bottom ? 1 : 0)) { H = e.H; break; }
-    if (!H) return false;
+    int H = 0, mode = bottom ? 1 : 0;
+    long long R = 0;
+    for (const auto& e : kDispatch16) if (32 * e.H >= max_rows + (bottom ? 1 : 0)) { H = e.H; R = 32LL * e.H; break; }
+    if (!H) {
+        if (!bottom) return false;
+        mode = 2;
+        for (const auto& e : kDispatch16m) {
+            const long long sl = 32LL * e.H, slots = (max_rows + 1 + sl - 1) / sl * sl;
+            if (R == 0 || slots < R || (slots == R && e.H > H)) { R = slots; H = e.H; }
+        }
+    }
     Fast16 f;
     f.D16 = 16 * D; f.beta = beta;
     f.tlo = (uint32_t)f.D16 * 0x01010100u; f.thi = (uint32_t)f.D16 * 0x01010101u;
@@ -224,7 +235,7 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     // mismatches -- linear in (i, j), so its extreme is at a corner -- plus one gap opening for the
     // Ix / Iy states.  Dead slots idle between `neg` and neg - (H*D16 + one penalty): each dead row
     // is at most one mismatch below the row above it, and the top one is fed the constant `neg`.
-    const long long R = 32LL * H, C = max_cols;
+    const long long C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
     const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
     if (pen_o > 3000 || pen_e > 3000) return false;
@@ -238,7 +249,7 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     if (bias - lower < neg + 256) return false;
     f.bias = (int32_t)bias; f.neg = (int32_t)neg;
     *out = f; *H_out = H;
-    *mode_out = bottom ? 1 : 0;
+    *mode_out = mode;
     return true;
 }
 
@@ -252,7 +263,10 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H, &mode);
     if (!fast) H = pick_H(max_rows);
     const Dispatch* d = nullptr;
-    if (fast) { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
+    if (fast) {
+        if (mode == 2) { for (const auto& e : kDispatch16m) if (e.H == H) d = &e; }
+        else { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
+    }
     else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
     // occupancy of each kernel variant is queried once per process
     static std::map<const Dispatch*, int> occupancy_cache;
@@ -265,7 +279,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     }
     if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
     const long long SL = 32LL * H;
-    const long long nstripes = fast ? 1 : (max_rows + SL - 1) / SL;
+    const long long nstripes = fast ? (mode == 2 ? (max_rows + 1 + SL - 1) / SL : 1) : (max_rows + SL - 1) / SL;
     const long long per_warp = ((nstripes * (max_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (max_cols + 2);
     const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;

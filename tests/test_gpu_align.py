@@ -74,7 +74,7 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
             engine.set_option("force_general", 0)
             engine.set_option("force_top", 0)
     if expect_fast is True:
-        assert 16 in kernels, "packed fast path was expected to be eligible"
+        assert kernels & {16, 17, 18}, "packed fast path was expected to be eligible"
     if expect_fast is False:
         assert kernels == {32}
 
@@ -154,12 +154,26 @@ def test_extra_symbols(engine):
 
 
 def test_multi_stripe_long_pairs(engine):
-    """Lengths above one 32*H stripe: rows cross the stripe-boundary buffer."""
+    """Lengths above one 32*H stripe: rows cross the stripe-boundary buffer (general kernel and
+    the multi-stripe packed kernel)."""
     rng = np.random.default_rng(1500)
     xs, ys = random_pairs(rng, 12, 1100, 1700, sub=0.1, indel=0.02)
-    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1))
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+    assert_kernel(engine, xs, ys, (1, -1, -8, -1, -1, -1), 18)
     xs, ys = random_pairs(rng, 3, 2500, 3300, sub=0.1, indel=0.02)
-    check_pairs(engine, xs, ys, (2, -1, -3, -2, -1, -1))
+    check_pairs(engine, xs, ys, (2, -1, -3, -2, -1, -1), expect_fast=False)   # beyond the 16-bit window
+    # BASELINE config C5 geometry: mixed 300-1500 bp in one launch, neighbours of any length
+    xs, ys = random_pairs(rng, 40, 300, 1500, sub=0.1, indel=0.02)
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), strings=False, expect_fast=True)
+    assert_kernel(engine, xs, ys, (1, -1, -8, -1, -1, -1), 18)
+
+
+def assert_kernel(engine, xs, ys, scores, kernel):
+    engine.set_scores(scores)
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    engine.align_pairs(np.arange(len(xs), dtype=np.int32), np.arange(len(xs), dtype=np.int32), want=("score",))
+    assert engine.last_kernel == kernel
 
 
 def test_ragged_and_tiny(engine):
