@@ -235,6 +235,9 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     // mismatches -- linear in (i, j), so its extreme is at a corner -- plus one gap opening for the
     // Ix / Iy states.  Dead slots idle between `neg` and neg - (H*D16 + one penalty): each dead row
     // is at most one mismatch below the row above it, and the top one is fed the constant `neg`.
+    // (bottom-aligned variants pad ABOVE row 0 with dead slots, so their DP has max_rows real rows;
+    //  the top-aligned variant pads below row nA with rows that extend the DP)
+    if (mode != 0) R = max_rows;
     const long long C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
     const long long pen_o = std::max({f.PoX, f.PeoX, f.PoY, f.PeoY});
