@@ -1,6 +1,7 @@
 """Throughput probes for the other BASELINE configs at reduced pair counts (same sequence
 geometry): C4 = versusReference best match (queries x references, device-side first minimum),
-C5 = mixed 300-1500 bp all-vs-all (rows split by length between the packed and general kernels).
+C5 = mixed 300-1500 bp all-vs-all (rows grouped by length: one packed-kernel launch per stripe
+geometry, the multi-stripe packed kernel above 1023 bp).
 Prints one JSON line per config."""
 import json
 import sys
@@ -47,4 +48,4 @@ for it in range(2):
 cells = sum(map(len, mixed)) ** 2
 short = sum(len(s) <= 1023 for s in mixed)
 print(json.dumps(dict(config="C5 (reduced): 1536 sequences of 300-1500 bp, all ordered pairs", pairs=n * n, seconds=round(dt, 4),
-                      pairs_per_s=n * n / dt, gcups=cells / dt / 1e9, kernel=eng.last_kernel, rows_packed=short, rows_general=n - short)))
+                      pairs_per_s=n * n / dt, gcups=cells / dt / 1e9, kernel=eng.last_kernel, rows_single_stripe=short, rows_multi_stripe=n - short)))
