@@ -315,3 +315,39 @@ def test_mixed_length_rectangle_splits_rows(engine):
     assert_metrics_close(got["metrics"].reshape(-1, 4), want["metrics"])
     assert np.array_equal(sub["counts"], got["counts"][3:14, 2:9])
     assert np.array_equal(sub["score"], got["score"][3:14, 2:9])
+
+
+def test_stripe_boundary_lengths(engine):
+    """Lengths on both sides of every geometry threshold (rows per lane x 32, with and without the
+    spare border slot of the bottom-aligned variant), all combinations, all kernel variants."""
+    rng = np.random.default_rng(1023)
+    lengths = [1, 2, 31, 32, 33, 255, 256, 257, 383, 384, 511, 512, 513, 671, 672, 673, 767, 768, 1022, 1023, 1024, 1025, 1343, 1344, 1345]
+    base = rng.integers(0, 4, size=1400)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def variant(n):
+        s = alpha[base[:n]].copy()
+        hit = rng.random(n) < 0.08
+        s[hit] = alpha[rng.integers(0, 4, size=int(hit.sum()))]
+        if n > 40:
+            cut = int(rng.integers(5, n - 20))
+            s = np.concatenate([s[:cut], s[cut + 3:], alpha[rng.integers(0, 4, size=3)]])   # a 3-base deletion, length kept
+        return s.tobytes()
+
+    xs, ys = [], []
+    for la in lengths:
+        for lb in (1, 33, 672, 1023, 1345, la):
+            xs.append(variant(la))
+            ys.append(variant(lb))
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), strings=False, expect_fast=True)
+    # pairs in launch order share warps two by two: also run each boundary length on its own
+    for la in (671, 672, 1023, 1024):
+        check_pairs(engine, [variant(la)] * 3, [variant(la + d) for d in (-1, 0, 1)], (1, -1, -8, -1, -1, -1), expect_fast=True)
+
+
+def test_extreme_but_eligible_scores(engine):
+    """Largest penalties / match bonus the packed kernel accepts, and non-default end-gap costs."""
+    rng = np.random.default_rng(77)
+    xs, ys = random_pairs(rng, 120, 1, 300, sub=0.2, indel=0.05)
+    for scores in [(7, 0, -60, -9, -30, -9), (3, -4, -90, -1, -1, -1), (1, -1, -8, -1, -8, -1), (0, -1, -3, -1, -2, -1), (2, -5, -20, -3, -1, -3)]:
+        check_pairs(engine, xs, ys, scores, strings=False, expect_fast=True)
