@@ -352,7 +352,11 @@ def test_extreme_but_eligible_scores(engine):
     rng = np.random.default_rng(77)
     xs, ys = random_pairs(rng, 120, 1, 300, sub=0.2, indel=0.05)
     check_pairs(engine, xs, ys, (7, 0, -60, -9, -30, -9), strings=False, expect_fast=False)
-    for scores in [(3, -4, -90, -1, -1, -1), (1, -1, -8, -1, -8, -1), (0, -1, -3, -1, -2, -1), (2, -5, -20, -3, -1, -3)]:
+    for scores in [(1, -1, -8, -1, -8, -1), (0, -1, -3, -1, -2, -1)]:
         check_pairs(engine, xs, ys, scores, strings=False, expect_fast=True)
+    # cheap end gaps next to expensive mismatches: adjacent opposite gaps can be co-optimal, so the
+    # restricted recurrence is not provably exact and the host must keep these on the general kernel
+    for scores in [(3, -4, -90, -1, -1, -1), (2, -5, -20, -3, -1, -3)]:
+        check_pairs(engine, xs, ys, scores, strings=False, expect_fast=False)
     xs, ys = random_pairs(rng, 120, 1, 60, sub=0.2, indel=0.05)
     check_pairs(engine, xs, ys, (7, 0, -60, -9, -30, -9), expect_fast=True)   # same scores fit at 60 bp
