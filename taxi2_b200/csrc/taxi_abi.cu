@@ -283,8 +283,12 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
     const long long SL = 32LL * H;
     const long long nstripes = fast ? (mode == 2 ? (max_rows + 1 + SL - 1) / SL : 1) : (max_rows + SL - 1) / SL;
-    const long long per_warp = ((nstripes * (max_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
-    const long long bnd_per_warp = 2LL * (max_cols + 2);
+    // Size the arena for the longest column sequence of the loaded set, not just of this launch:
+    // growing it later means cudaFree + cudaMalloc of ~1 GB, a device-wide synchronisation that
+    // costs tens to hundreds of milliseconds when several ranks share the driver.
+    const long long arena_cols = std::max<long long>(max_cols, yset(c).maxlen);
+    const long long per_warp = ((nstripes * (arena_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
+    const long long bnd_per_warp = 2LL * (arena_cols + 2);
     const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;
     c->last_kernel = fast ? 16 + mode : 32;
     a.f16 = f16;
