@@ -286,7 +286,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     // Size the arena for the longest column sequence of the loaded set, not just of this launch:
     // growing it later means cudaFree + cudaMalloc of ~1 GB, a device-wide synchronisation that
     // costs tens to hundreds of milliseconds when several ranks share the driver.
-    const long long arena_cols = std::max<long long>(max_cols, yset(c).maxlen);
+    const long long arena_cols = (std::max<long long>(max_cols, yset(c).maxlen) + 255) / 128 * 128;   // + headroom for reloaded sets
     const long long per_warp = ((nstripes * (arena_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (arena_cols + 2);
     const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;
