@@ -325,7 +325,10 @@ def main() -> None:
             config=workload_config(world),
             roofline=dict(
                 bound="int32_alu", kernel=kernel_name, achieved=achieved / 1e9, peak=peak / 1e9, unit="Gop/s",
-                frac=achieved / peak, traffic=None,
+                frac=achieved / peak,
+                # DRAM bytes per launch: ncu --set full measured 1.31 B/cell (1.17 written + 0.14 read) for this kernel
+                # (profiles/ncu_gotoh_pair16_21_r01.json), scaled to this launch's cells
+                traffic=(1.31 if kernel_id in (16, 17) else 1.42) * cells_per_launch,
                 how=f"{OPS_PER_CELL} algorithmic INT32 ops/cell x {cells_per_launch:.3e} cells/launch / {launch_s * 1e3:.1f} ms (CUDA events on the launch stream); peak {peak_how}",
                 hbm=dict(achieved=cells_per_launch * trace_bytes_per_cell / launch_s / 1e9, peak=peak_hbm(), unit="GB/s",
                          note="algorithmic HBM traffic of the same kernel: traceback codes written once; read back sparsely"),
