@@ -68,3 +68,13 @@ def test_metrics_exact():
 def test_zero_distance_is_positive_zero():
     m = oracle.metrics(oracle.count("ACGT", "ACGT"))
     assert all(v == 0.0 and math.copysign(1.0, v) == 1.0 for v in m)
+
+
+def test_biopython_tutorial_example_first_alignment():
+    """Soft pin of the Needleman-Wunsch path order (horizontal, vertical, diagonal): the Biopython
+    tutorial's own example, `PairwiseAligner().align("GAACT", "GAT")` with the default scores
+    (match 1, everything else 0), prints `GA--T` first and `G-A-T` second.  Quoted from the
+    published documentation (Biopython is not installable here), so this is weaker than a
+    reference fixture, but it is the only public witness of the tie-breaking order."""
+    ax, ay, score = oracle.align("GAACT", "GAT", (1, 0, 0, 0, 0, 0))
+    assert (ax, ay, score) == ("GAACT", "GA--T", 3.0)
