@@ -2,8 +2,8 @@
 included), alignment + the selected metrics, with the reference's output files.
 
 Mirrors /root/reference/src/itaxotools/taxi2/tasks/versus_all.py (attribute surface :374-415,
-pipeline :732-773, writers :98-350).  Differences, all out of the hot-path scope:
-per-sequence statistics files (stats/*.tsv) and histogram plots are not produced.
+pipeline :732-773, writers :98-350, statistics files :448-520).  Difference, out of the hot-path
+scope: histogram plots are not produced.
 """
 from __future__ import annotations
 
@@ -21,6 +21,7 @@ from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..handlers import FileHandler
 from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, Sequences
+from ..statistics import StatisticsCalculator, StatisticsHandler
 from ..types import AttrDict
 from .common import ComparisonType, Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none
 
@@ -126,6 +127,9 @@ class VersusAll:
         assert self.work_dir
         w = Path(self.work_dir)
         self.paths.summary = w / "summary.tsv"
+        self.paths.stats_all = w / "stats" / "all.tsv"
+        self.paths.stats_species = w / "stats" / "species.tsv"
+        self.paths.stats_genera = w / "stats" / "genera.tsv"
         self.paths.aligned_pairs = w / "align" / "aligned_pairs.txt"
         self.paths.distances_linear = w / "distances" / "linear.tsv"
         self.paths.distances_matricial = w / "distances" / "matricial"
@@ -136,6 +140,32 @@ class VersusAll:
         self.params.distances.metrics = self.params.distances.metrics or [
             DistanceMetric.Uncorrected(), DistanceMetric.UncorrectedWithGaps(),
             DistanceMetric.JukesCantor(), DistanceMetric.Kimura2P()]
+
+    # -- stats/*.tsv (versus_all.py:448-520): one pass over the (normalized) sequences ---------------
+    def write_statistics(self, sequences: list[Sequence]) -> None:
+        p = self.params
+        options = dict(float_formatter=p.format.float, percentage_formatter=p.format.percentage,
+                       percentage_multiply=p.format.percentage_multiply)
+        if p.stats.all:
+            create_parents(self.paths.stats_all)
+            with StatisticsHandler.Single(self.paths.stats_all, "w", **options) as file:
+                file.write(StatisticsCalculator(s.seq.upper() for s in sequences).calculate())
+        for partition, enabled, name, path in ((self.input.species, p.stats.species, "species", self.paths.stats_species),
+                                               (self.input.genera, p.stats.genera, "genera", self.paths.stats_genera)):
+            if not partition or not enabled:
+                continue
+            calculators = {}
+            for subset in partition.values():          # groups in the partition's own order
+                if subset not in calculators:
+                    calculators[subset] = StatisticsCalculator(group=subset)
+            for s in sequences:
+                subset = partition.get(s.id, None)
+                if subset is not None:
+                    calculators[subset].add(s.seq.upper())
+            create_parents(path)
+            with StatisticsHandler.Groups(path, "w", group_name=name, **options) as file:
+                for calc in calculators.values():
+                    file.write(calc.calculate())
 
     # -- the run -----------------------------------------------------------------------------------
     def start(self) -> Results:
@@ -153,6 +183,7 @@ class VersusAll:
         sequences = list(self.input.sequences.normalize() if p.pairs.align else self.input.sequences)
         n = len(sequences)
         engine = default_engine(self.device)
+        self.write_statistics(sequences)
 
         writers = []
         pairs_file = linear_file = None

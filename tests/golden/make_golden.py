@@ -10,6 +10,9 @@ Sources (relative to /root/reference):
   tests/test_pairs/simple.*           -> pairs_simple.{tsv,formatted}
   samples/Taxi2test1_{10,50,120}.tab  -> sample inputs for parity runs
   tests/test_distances/*, tests/test_sequences/* (tsv, fas) -> distances/, sequences/ (handler fixtures)
+  tests/test_statistics.py:113-250    -> statistics_cases.json (17 count + 108 statistic vectors)
+  tests/test_statistics/*             -> statistics/ (writer fixtures)
+  samples/Taxi2test1_ca200.tab        -> un-aligned 200-row resample for the align=False parity run
 
 The reference test modules cannot be imported here (Bio / itaxotools.* are absent), so the
 tables are read with `ast` instead of being executed.
@@ -82,8 +85,28 @@ def handler_fixtures():
         shutil.copyfile(REF / "tests/test_sequences" / name, OUT / "sequences" / name)
 
 
+def statistics_cases():
+    """CountTest(...) / StatisticTest(...) rows of tests/test_statistics.py; the argument
+    expressions ("A" * 100, list(map(lambda ...)), sqrt(8 / 3)) are evaluated, nothing else is."""
+    from math import sqrt
+    tree = ast.parse((REF / "tests/test_statistics.py").read_text())
+    env = {"sqrt": sqrt, "list": list, "map": map, "range": range}
+    value = lambda node: eval(compile(ast.Expression(node), "<case>", "eval"), {"__builtins__": {}}, env)  # noqa: E731
+    out = {"counts": [], "statistics": []}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.args:
+            if node.func.id == "CountTest":
+                out["counts"].append({"count": value(node.args[0]), "fixed": value(node.args[1]), "sequence": value(node.args[2])})
+            elif node.func.id == "StatisticTest" and isinstance(node.args[0], ast.Attribute):
+                out["statistics"].append({"stat": node.args[0].attr, "fixed": value(node.args[1]), "sequences": value(node.args[2])})
+    (OUT / "statistics").mkdir(exist_ok=True)
+    for path in sorted((REF / "tests/test_statistics").iterdir()):
+        shutil.copyfile(path, OUT / "statistics" / path.name)
+    return out
+
+
 def samples():
-    for name in ("Taxi2test1_10", "Taxi2test1_50", "Taxi2test1_120"):
+    for name in ("Taxi2test1_10", "Taxi2test1_50", "Taxi2test1_120", "Taxi2test1_ca200"):
         shutil.copyfile(REF / "samples" / f"{name}.tab", OUT / f"{name}.tab")
 
 
@@ -92,6 +115,7 @@ if __name__ == "__main__":
     (OUT / "metrics_cases.json").write_text(json.dumps(metric_cases(), indent=1) + "\n")
     for name in ("simple.tsv", "simple.formatted"):
         shutil.copyfile(REF / "tests/test_pairs" / name, OUT / f"pairs_{name}")
+    (OUT / "statistics_cases.json").write_text(json.dumps(statistics_cases(), indent=1) + "\n")
     samples()
     handler_fixtures()
     print("golden fixtures written to", OUT)

@@ -30,6 +30,56 @@ def oracle_align(pair: SequencePair, scores=None) -> SequencePair:
     return SequencePair(Sequence(pair.x.id, ax, pair.x.extras), Sequence(pair.y.id, ay, pair.y.extras))
 
 
+STAT_LABELS = ["Total number of sequences", "Total length of all sequences ", "Number of sequences with 0 bp",
+               "Number of sequences with less than 100 bp", "Number of sequences between 101-300 bp",
+               "Number of sequences between 301-1000 bp", "Number of sequences with more than 1000 bp", "Minimum sequence length",
+               "Maximum sequence length ", "Mean sequence length  ", "Median sequence length  ", "Standard deviation of sequence length",
+               "Percentage of base A", "Percentage of base C", "Percentage of base G", "Percentage of base T", "GC content",
+               "Percentage of ambiguity codes", "Percentage of missing data ", "Percentage of missing data including gaps",
+               "Percentage of gaps", "N50 statistic", "L50 statistic", "N90 statistic", "L90 statistic"]
+
+
+def stat_values(seqs: list[str], ffmt: str, pfmt: str, multiply: bool) -> list[str]:
+    """The 25 statistics of a list of upper-case strings as text, computed with numpy straight
+    from the definitions in /root/reference/src/itaxotools/taxi2/statistics.py:45-224."""
+    import numpy as np
+    joined = "".join(seqs)
+    cnt = {ch: joined.count(ch) for ch in "-NACGT"}
+    lens = np.array([len(s) - s.count("-") for s in seqs], dtype=np.int64)
+    n, nuc, tot = len(seqs), int(lens.sum()), len(joined)
+
+    def nl(arg):
+        if not lens.any():
+            return 0, 0
+        d = np.sort(lens)[::-1]
+        pos = int(np.argmax(np.cumsum(d) >= d.sum() * arg / 100))
+        return int(d[pos]), pos + 1
+    ints = [n, nuc, int((lens == 0).sum()), int(((lens > 0) & (lens <= 100)).sum()), int(((lens > 100) & (lens <= 300)).sum()),
+            int(((lens > 300) & (lens <= 1000)).sum()), int((lens > 1000).sum()), int(lens.min()) if n else 0, int(lens.max()) if n else 0]
+    from statistics import median, pstdev
+    floats = [nuc / n if n else 0.0, float(median(lens.tolist())) if n else 0.0, float(pstdev(lens.tolist())) if n > 1 else 0.0]
+    frac = lambda v, d: (v / d if d else 0.0) * (100 if multiply else 1)  # noqa: E731
+    amb = nuc - cnt["N"] - cnt["A"] - cnt["C"] - cnt["G"] - cnt["T"]
+    pct = [frac(cnt["A"], nuc), frac(cnt["C"], nuc), frac(cnt["G"], nuc), frac(cnt["T"], nuc), frac(cnt["C"] + cnt["G"], nuc),
+           frac(amb, nuc), frac(cnt["N"], nuc), frac(cnt["N"] + cnt["-"], tot), frac(cnt["-"], tot)]
+    return [*map(str, ints), *(ffmt.format(v) for v in floats), *(pfmt.format(v) for v in pct), *map(str, nl(50) + nl(90))]
+
+
+def write_stats(seqs, work: Path, species, genera, ffmt: str, pfmt: str = "{:.2f}", multiply: bool = False) -> None:
+    (work / "stats").mkdir(parents=True, exist_ok=True)
+    with FileHandler.Tabfile(work / "stats" / "all.tsv", "w") as f:
+        for row in zip(STAT_LABELS, stat_values([s.seq.upper() for s in seqs], ffmt, pfmt, multiply)):
+            f.write(row)
+    for name, part in (("species", species), ("genera", genera)):
+        if not part:
+            continue
+        with FileHandler.Tabfile(work / "stats" / f"{name}.tsv", "w") as f:
+            f.write((name, *STAT_LABELS))
+            for group in dict.fromkeys(part.values()):
+                members = [s.seq.upper() for s in seqs if part.get(s.id, None) == group]
+                f.write((group, *stat_values(members, ffmt, pfmt, multiply)))
+
+
 COMPARISON = {(None, None): "no info", (None, True): "intra-species", (None, False): "inter-species",
               (False, None): "inter-genus", (False, True): "inter-genus", (False, False): "inter-genus",
               (True, None): "intra-genus", (True, True): "intra-species", (True, False): "inter-species"}
@@ -42,6 +92,7 @@ def versus_all(sequences, work: Path, species=None, genera=None, align=True, met
     (work / "align").mkdir(parents=True, exist_ok=True)
     (work / "distances" / "matricial").mkdir(parents=True, exist_ok=True)
     seqs = [s.normalize() for s in sequences] if align else list(sequences)
+    write_stats(seqs, work, species, genera, fmt, multiply=multiply)
     text = lambda v: missing if v is None else fmt.format(v)  # noqa: E731
     aggs = {name: {str(m): {} for m in metrics} for name in ("genera", "species")}
     with SequencePairHandler.Formatted(work / "align" / "aligned_pairs.txt", "w") as pairs_file, \

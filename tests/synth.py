@@ -67,8 +67,8 @@ def random_pairs(rng, n: int, lo: int, hi: int, sub: float = 0.15, indel: float 
     return xs, ys
 
 
-def read_tab_sequences(path) -> tuple[list[str], list[str]]:
-    """ids and NORMALIZED sequences of a TaxI2 sample .tab (seqid ... sequence)."""
+def read_tab_sequences(path, normalize: bool = True) -> tuple[list[str], list[str]]:
+    """ids and sequences (normalized unless told otherwise) of a TaxI2 sample .tab (seqid ... sequence)."""
     ids, seqs = [], []
     with open(path, "r", encoding="utf-8", errors="surrogateescape") as f:
         header = f.readline().rstrip("\n").split("\t")
@@ -79,5 +79,5 @@ def read_tab_sequences(path) -> tuple[list[str], list[str]]:
                 continue
             row = line.split("\t")
             ids.append(row[ci])
-            seqs.append(row[cs].replace("?", "N").replace("-", "").upper())
+            seqs.append(row[cs].replace("?", "N").replace("-", "").upper() if normalize else row[cs])
     return ids, seqs

@@ -249,6 +249,28 @@ def test_prealigned_counts(engine):
             assert tuple(rect["counts"][i, j]) == tuple(c)
 
 
+def test_alignment_free_on_the_ca200_sample(engine):
+    """BASELINE config 2 in its runnable form (SURVEY.md 8d, C2 plan i): the reference's 200-row
+    resample, un-aligned (26 distinct lengths, lower case + n), params.pairs.align = False ->
+    the raw strings go straight into the counting kernel.  All 40 000 ordered pairs vs the oracle."""
+    from synth import read_tab_sequences
+    ids, seqs = read_tab_sequences(GOLDEN / "Taxi2test1_ca200.tab", normalize=False)
+    assert len(seqs) == 200 and len({len(s) for s in seqs}) > 20
+    engine.load(seqs, 0)
+    got = engine.count_rect(0, 200, 0, 200)
+    text = [s.decode() if isinstance(s, bytes) else s for s in seqs]
+    distinct = {}
+    for i in range(200):
+        for j in range(200):
+            key = (text[i], text[j])
+            if key not in distinct:
+                c = oracle.count(*key) or (0, 0, 0, 0)
+                distinct[key] = (tuple(c), np.array(oracle.metrics(c)))
+            want_c, want_m = distinct[key]
+            assert tuple(got["counts"][i, j]) == want_c, (ids[i], ids[j])
+            assert_metrics_close(got["metrics"][i, j][None, :], want_m[None, :])
+
+
 def test_full_size_tile_properties(engine):
     """BASELINE C3 geometry (650 bp, 384 x 384 ordered pairs = 6.2e10 cells): too large for the CPU
     oracle, so check size-independent properties -- the three kernel variants agree bit for bit,
