@@ -43,13 +43,16 @@ int fail(int code, const char* fmt, ...)
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
-    cudaError_t reserve(size_t n)
+    // grow-only; `slack` (in 1/8ths) over-allocates so that a slightly larger next request
+    // (the next tile's sequences) does not cost a cudaFree + cudaMalloc pair
+    cudaError_t reserve(size_t n, int slack = 0)
     {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        const size_t want = std::max<size_t>(n + n / 8 * (size_t)slack, 1);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -518,8 +521,8 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
     s.n = n;
     s.total = s.off[n];
     if (s.total > 0 && !bytes) return fail(TAXI_E_ARG, "null bytes");
-    CUDA_TRY(s.bytes.reserve((size_t)s.total + 16));
-    CUDA_TRY(s.d_off.reserve((size_t)n + 1));
+    CUDA_TRY(s.bytes.reserve((size_t)s.total + 16, 1));
+    CUDA_TRY(s.d_off.reserve((size_t)n + 1, 1));
     if (s.total) CUDA_TRY(cudaMemcpyAsync(s.bytes.p, bytes, (size_t)s.total, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(s.d_off.p, s.off.data(), ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     // symbol codebook (host scan, O(total)); a new row set starts a new codebook
@@ -542,7 +545,7 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
         CUDA_TRY(c->d_codebook.reserve(256));
         CUDA_TRY(cudaMemcpyAsync(c->d_codebook.p, book, 256, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // `book` is a stack buffer
-        CUDA_TRY(s.codes.reserve((size_t)s.total + 16));
+        CUDA_TRY(s.codes.reserve((size_t)s.total + 16, 1));
         if (s.total) {
             encode_codes_kernel<<<(unsigned)std::min<int64_t>((s.total + 255) / 256, 4096), 256, 0, c->stream>>>(s.bytes.p, s.total, c->d_codebook.p, s.codes.p);
             CUDA_TRY(cudaGetLastError());
@@ -551,7 +554,7 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
         // which is still right for every symbol set 0 contains
     }
     s.W = std::max(1, (s.maxlen + 31) / 32);
-    CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * 4 * s.W));
+    CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * 4 * s.W, 1));
     if (n > 0) {
         const long long total = (long long)n * s.W;
         pack_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s.bytes.p, s.d_off.p, n, s.W, s.planes.p);
