@@ -164,7 +164,9 @@ void taxi_host_free(void* p);
  * Options: "force_general" = 1 routes every alignment through the general int32 kernel
  * (the packed 16-bit fast path is only taken when it is provably exact for the score set and
  * lengths; this switch exists so tests can compare the two); "force_top" = 1 keeps the packed
- * kernel on its top-aligned variant.  taxi_last_kernel() reports which kernel the last alignment
+ * kernel on its top-aligned variant; "sort_columns" = 0 stops rectangle calls from visiting
+ * columns of unequal length longest first (a scheduling choice only: results and their
+ * positions are the same either way).  taxi_last_kernel() reports which kernel the last alignment
  * call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 top-aligned, 17 = gotoh_pair16
  * bottom-aligned, 18 = gotoh_pair16 bottom-aligned in several stripes (x longer than 1023),
  * 48 = a rectangle whose rows were grouped by length into several launches.

@@ -45,6 +45,9 @@ struct AlignArgs {
     int32_t x0, y0, ny;                       // rect mode: pair p = (x0 + p / ny, y0 + p % ny)
     const int32_t* xrows;                     // rect mode, optional: row r of the launch is sequence xrows[r] (a subset of the
                                               // rectangle's rows); results still land at ((x - x0) * ny + y)
+    const int32_t* ycols;                     // rect mode, optional: column c of the launch is sequence ycols[c] (a permutation
+                                              // of the rectangle's columns, longest first, so that the two pairs of a warp and
+                                              // consecutive work units have similar lengths)
     long long npairs;
     ScoreSet sc;
     int32_t* score;                           // [npairs] or nullptr
@@ -64,8 +67,8 @@ __device__ __forceinline__ PairIndex pair_index(const AlignArgs& a, long long p)
     if (a.px) { r.xi = a.px[p]; r.yi = a.py[p]; r.out = p; return r; }
     const int row = (int)(p / a.ny), col = (int)(p % a.ny);
     r.xi = a.xrows ? a.xrows[row] : a.x0 + row;
-    r.yi = a.y0 + col;
-    r.out = (long long)(r.xi - a.x0) * a.ny + col;
+    r.yi = a.ycols ? a.ycols[col] : a.y0 + col;
+    r.out = (long long)(r.xi - a.x0) * a.ny + (r.yi - a.y0);
     return r;
 }
 

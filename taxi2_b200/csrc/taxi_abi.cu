@@ -90,13 +90,14 @@ struct taxi_ctx {
     DevBuf<uint8_t> d_codebook;
     int force_general = 0;          // option: always use the general int32 kernel
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
+    int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
     DevBuf<uint8_t> trace;
     DevBuf<int32_t> bnd;
     DevBuf<unsigned long long> counter;
     DevBuf<int> status;
-    DevBuf<int32_t> d_px, d_py, d_xrows;
+    DevBuf<int32_t> d_px, d_py, d_xrows, d_ycols;
     DevBuf<int32_t> d_score, d_counts;
     DevBuf<double> d_metrics;
     DevBuf<uint8_t> d_alnx, d_alny;
@@ -354,7 +355,7 @@ void fill_rect(AlignArgs& a, const taxi_ctx* c, int32_t x0, int32_t y0, int32_t 
     a.xb = X.bytes.p; a.xoff = X.d_off.p;
     a.yb = Y.bytes.p; a.yoff = Y.d_off.p;
     a.xc = X.codes.p; a.yc = Y.codes.p;
-    a.px = a.py = nullptr; a.xrows = nullptr;
+    a.px = a.py = nullptr; a.xrows = nullptr; a.ycols = nullptr;
     a.x0 = x0; a.y0 = y0; a.ny = ny; a.npairs = npairs;
 }
 
@@ -477,7 +478,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); }
     c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
-    c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
+    c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
     c->d_argidx.release(); c->d_argval.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -591,6 +592,29 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
     a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
     c->cells += cells_rect(c->set[0], yset(c), x0, nx, y0, ny);
+
+    // Columns of unequal length: a warp sweeps max(len_y) columns for its two pairs, so pairing a
+    // short column with a long one idles half the lanes' work.  Columns are visited longest first
+    // (stable), which pairs similar lengths and hands the longest units out first.
+    {
+        const SeqSet& Y = yset(c);
+        int lo = INT32_MAX, hi = 0;
+        for (int32_t j = y0; j < y0 + ny; ++j) {
+            const int len = (int)(Y.off[j + 1] - Y.off[j]);
+            lo = std::min(lo, len); hi = std::max(hi, len);
+        }
+        if (c->sort_columns && ny > 2 && hi - lo > hi / 16) {
+            std::vector<int32_t> cols((size_t)ny);
+            for (int32_t j = 0; j < ny; ++j) cols[(size_t)j] = y0 + j;
+            std::stable_sort(cols.begin(), cols.end(), [&](int32_t u, int32_t v) {
+                return Y.off[u + 1] - Y.off[u] > Y.off[v + 1] - Y.off[v];
+            });
+            CUDA_TRY(c->d_ycols.reserve((size_t)ny, 1));
+            CUDA_TRY(cudaMemcpyAsync(c->d_ycols.p, cols.data(), cols.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));   // `cols` is a host vector about to go out of scope
+            a.ycols = c->d_ycols.p;
+        }
+    }
 
     // Mixed lengths (BASELINE config C5).  The packed kernel keeps 32*H row slots per pair, so a
     // rectangle whose rows differ a lot in length wastes slots -- and rows longer than one stripe
@@ -857,6 +881,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (!c || !key) return fail(TAXI_E_ARG, "null argument");
     if (std::strcmp(key, "force_general") == 0) { c->force_general = value; return TAXI_OK; }
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
+    if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }
 
