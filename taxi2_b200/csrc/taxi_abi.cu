@@ -616,47 +616,65 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
         }
     }
 
-    // Mixed lengths (BASELINE config C5).  The packed kernel keeps 32*H row slots per pair, so a
-    // rectangle whose rows differ a lot in length wastes slots -- and rows longer than one stripe
-    // cannot use it at all.  Rows are therefore grouped by the smallest kernel geometry that holds
-    // them (packed H = 8..32, else the general kernel) and every group gets its own launch over a
-    // row list; results still land in the rectangle's row-major positions.
+    // Mixed lengths (BASELINE config C5).  The packed kernel keeps 32*H row slots per stripe, so a
+    // rectangle whose rows differ a lot in length wastes slots.  Rows are therefore grouped by the
+    // kernel geometry that wastes the fewest slots for them -- one stripe of H = 8..32 rows per
+    // lane, or several stripes of H = 16..32 above 1023 bp -- and every group gets its own launch
+    // over a row list (longest rows first); results still land in the rectangle's row-major positions.
     {
         const SeqSet& X = c->set[0];
         const bool bottom = (c->raw_scores[3] == c->raw_scores[5]) && !c->force_top;
         constexpr int K = (int)(sizeof(kDispatch16) / sizeof(kDispatch16[0]));
-        std::vector<int32_t> rows[K + 1];
-        int maxlen[K + 1] = {0};
+        constexpr int M = (int)(sizeof(kDispatch16m) / sizeof(kDispatch16m[0]));
+        std::vector<int32_t> rows[K + M];
+        int maxlen[K + M] = {0};
         for (int32_t i = x0; i < x0 + nx; ++i) {
             const int len = (int)(X.off[i + 1] - X.off[i]);
             int k = 0;
             while (k < K && 32 * kDispatch16[k].H - (bottom ? 1 : 0) < len) ++k;
+            if (k == K) {   // several stripes: same rule as fast16_eligible (fewest slots, ties -> larger H)
+                long long best = 0;
+                for (int m = 0; m < M; ++m) {
+                    const long long sl = 32LL * kDispatch16m[m].H, slots = (len + 1 + sl - 1) / sl * sl;
+                    if (best == 0 || slots <= best) { best = slots; k = K + m; }
+                }
+            }
             rows[k].push_back(i);
             maxlen[k] = std::max(maxlen[k], len);
         }
-        // fold small groups upwards (a launch should have enough pairs to fill the GPU)
+        // fold small groups (a launch should have enough pairs to fill the GPU): one-stripe groups
+        // into the next larger geometry, multi-stripe groups into the fullest multi-stripe group
         const long long min_pairs = 8LL * c->sms * 24;
-        for (int k = 0; k < K - 1; ++k) {
-            if (!rows[k].empty() && (long long)rows[k].size() * ny < min_pairs) {
-                rows[k + 1].insert(rows[k + 1].end(), rows[k].begin(), rows[k].end());
-                maxlen[k + 1] = std::max(maxlen[k + 1], maxlen[k]);
-                rows[k].clear();
-            }
-        }
+        auto fold = [&](int from, int to) {
+            rows[to].insert(rows[to].end(), rows[from].begin(), rows[from].end());
+            maxlen[to] = std::max(maxlen[to], maxlen[from]);
+            rows[from].clear();
+        };
+        for (int k = 0; k < K - 1; ++k)
+            if (!rows[k].empty() && (long long)rows[k].size() * ny < min_pairs) fold(k, k + 1);
+        int fullest = K;
+        for (int k = K; k < K + M; ++k) if (rows[k].size() > rows[fullest].size()) fullest = k;
+        for (int k = K; k < K + M; ++k)
+            if (k != fullest && !rows[k].empty() && (long long)rows[k].size() * ny < min_pairs) fold(k, fullest);
         int groups = 0;
-        for (int k = 0; k <= K; ++k) groups += !rows[k].empty();
+        for (int k = 0; k < K + M; ++k) groups += !rows[k].empty();
         Fast16 f16{};
         int H = 0, mode = 0;
         if (groups > 1 && !c->force_general && fast16_eligible(c, std::min(mr, 32 * 32 - 1), mc, &f16, &H, &mode)) {
             std::vector<int32_t> all;
             all.reserve((size_t)nx);
-            for (int k = 0; k <= K; ++k) all.insert(all.end(), rows[k].begin(), rows[k].end());
-            CUDA_TRY(c->d_xrows.reserve((size_t)nx));
+            for (int k = K + M - 1; k >= 0; --k) {   // the expensive groups first
+                std::stable_sort(rows[k].begin(), rows[k].end(), [&](int32_t u, int32_t v) {
+                    return X.off[u + 1] - X.off[u] > X.off[v + 1] - X.off[v];
+                });
+                all.insert(all.end(), rows[k].begin(), rows[k].end());
+            }
+            CUDA_TRY(c->d_xrows.reserve((size_t)nx, 1));
             CUDA_TRY(cudaMemcpyAsync(c->d_xrows.p, all.data(), all.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));   // `all` is a host vector about to go out of scope
             size_t at = 0;
             bool first = true;
-            for (int k = 0; k <= K; ++k) {
+            for (int k = K + M - 1; k >= 0; --k) {
                 if (rows[k].empty()) continue;
                 AlignArgs ak = a;
                 ak.xrows = c->d_xrows.p + at;
