@@ -67,9 +67,11 @@ template <int H> struct Pair16Geom {
 };
 
 // Warp-parallel first-path traceback over the 4-bit codes.  The walk is a chain of dependent
-// loads (each iteration needs the previous one's outcome), so the walks of the two pairs a warp
-// has just aligned advance in lockstep: both windows' loads are issued before either is consumed,
-// which halves the exposed memory latency.  (Speculatively loading the next straight-ahead window
+// loads (each iteration needs the previous one's outcome), so (1) the walks of the two pairs a
+// warp has just aligned advance in lockstep -- both windows' loads are issued before either is
+// consumed -- and (2) in state M an iteration fetches the two neighbouring diagonals along with
+// the main one, so that isolated one-column gaps (the common case in barcode data) do not cost
+// two more round trips each (walk_step).  (Speculatively loading the next straight-ahead window
 // as well was measured: 2 % slower, the extra loads cost more than the latency they hide.)
 struct Walk {
     const uint8_t* x; const uint8_t* y;   // ASCII of the two sequences
@@ -81,54 +83,72 @@ struct Walk {
     bool seen;
     int64_t wpos;                         // write cursor of the gapped strings
     int score;
-    int tb, ca, cb; bool valid;           // the window element this lane holds
+    // the window elements this lane holds.  In state M three diagonals are fetched at once:
+    // lane k has the cells (i-k, j-k) [main], (i-k-1, j-k) [one row up] and (i-k, j-k-1) [one
+    // column left], so that a one-column gap does not end the iteration (see walk_step)
+    int tb, ca, cb; bool valid;
+    int tbU, caU; bool validU;            // (i-k-1, j-k): x[i-k-2]; its y character is cb
+    int tbL, cbL; bool validL;            // (i-k, j-k-1): y[j-k-2]; its x character is ca
 };
 
+#ifndef TAXI_TB_DIAGONALS
+#define TAXI_TB_DIAGONALS 3
+#endif
+
 template <int H>
-__device__ __forceinline__ void walk_load(const Walk& w, int lane, const uint8_t* trace, int l0, int i, int j,
-                                          int& tb, int& ca, int& cb, bool& valid)
+__device__ __forceinline__ int trace_code(const Walk& w, const uint8_t* trace, int l0, int ii, int jj)
 {
     constexpr int HB = Pair16Geom<H>::HB;
-    const int di = (w.state != 2), dj = (w.state != 1);
-    const int ii = i - lane * di, jj = j - lane * dj;
-    valid = i > 0 && j > 0 && ii >= 1 && jj >= 1;
-    tb = 0; ca = 0; cb = 0;
-    if (valid) {
-        const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
-        const int st = slot / (32 * H), q = slot % (32 * H);   // stripe (0 for the single-stripe kernels)
-        const int l = q / H, r = q % H;
-        const int first = (st == 0) ? l0 : 0;                  // only the first stripe starts at a later lane
-        tb = (int)__ldcg(trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half);
-        ca = (int)__ldg(w.x + ii - 1);
-        cb = (int)__ldg(w.y + jj - 1);
-    }
+    const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
+    const int st = slot / (32 * H), q = slot % (32 * H);   // stripe (0 for the single-stripe kernels)
+    const int l = q / H, r = q % H;
+    const int first = (st == 0) ? l0 : 0;                  // only the first stripe starts at a later lane
+    return (int)__ldcg(trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half);
 }
 
 template <int H>
 __device__ __forceinline__ void walk_fetch(Walk& w, int lane, const uint8_t* trace, int l0)
 {
-    walk_load<H>(w, lane, trace, l0, w.i, w.j, w.tb, w.ca, w.cb, w.valid);
+    const int di = (w.state != 2), dj = (w.state != 1);
+    const int ii = w.i - lane * di, jj = w.j - lane * dj;
+    w.valid = w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1;
+    w.tb = 0; w.ca = 0; w.cb = 0;
+    w.tbU = w.caU = 0; w.validU = false;
+    w.tbL = w.cbL = 0; w.validL = false;
+    if (w.valid) {
+        w.tb = trace_code<H>(w, trace, l0, ii, jj);
+        w.ca = (int)__ldg(w.x + ii - 1);
+        w.cb = (int)__ldg(w.y + jj - 1);
+        if (TAXI_TB_DIAGONALS == 3 && w.state == 0) {
+            w.validU = ii >= 2;
+            w.validL = jj >= 2;
+            if (w.validU) { w.tbU = trace_code<H>(w, trace, l0, ii - 1, jj); w.caU = (int)__ldg(w.x + ii - 2); }
+            if (w.validL) { w.tbL = trace_code<H>(w, trace, l0, ii, jj - 1); w.cbL = (int)__ldg(w.y + jj - 2); }
+        }
+    }
 }
 
-__device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int lane)
+// Follow the path through one window: lane m holds the m-th cell the path would visit if it stayed
+// in w.state; the run ends at the first cell that hands over to another state (or at the window's
+// last valid cell).  Counts, strings and (i, j, state) are updated for the cells visited.
+__device__ __forceinline__ void walk_run(Walk& w, const AlignArgs& a, int lane, int tb, int ca, int cb, bool valid)
 {
-    if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
-    const int state = w.state, tb = w.tb;
+    const int state = w.state;
     const int di = (state != 2), dj = (state != 1);
     // state I would hand over to if the path reaches my cell in `state`
     int ns;
     if (state == 0) ns = 3 - (tb & 3);            // 3 -> M, 2 -> Ix, 1 -> Iy
     else if (state == 1) ns = (tb & 4) ? 0 : 1;   // Ix: opened from M, or extended
     else ns = (tb & 8) ? 0 : 2;                   // Iy
-    const unsigned cont = __ballot_sync(TAXI_FULL_MASK, w.valid && ns == state);
-    const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, w.valid);
+    const unsigned cont = __ballot_sync(TAXI_FULL_MASK, valid && ns == state);
+    const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, valid);
     const int f = __ffs(~cont) - 1;
     int V = (f < 0) ? 32 : f + 1;
     V = min(V, __popc(vmask));
     const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
     const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
-    const int ka = (state == 2) ? 4 : base_class(w.ca);
-    const int kb = (state == 1) ? 4 : base_class(w.cb);
+    const int ka = (state == 2) ? 4 : base_class(ca);
+    const int kb = (state == 1) ? 4 : base_class(cb);
     const bool both = ka < 4 && kb < 4;
     const int d = ka ^ kb;
     const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
@@ -148,12 +168,57 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
         w.pend += __popc(gm);
     }
     if (a.aln_x != nullptr && lane < V) {
-        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)w.ca;
-        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)w.cb;
+        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
+        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
     }
     w.wpos -= V;
     w.i -= V * di; w.j -= V * dj;
     w.state = next;
+}
+
+// One iteration on the data walk_fetch brought in.  In a gap state, or with single-diagonal
+// windows, that is one run.  In state M with the two neighbouring diagonals at hand the walk goes
+// on through one-column gaps without another (dependent, ~1 us) round trip to the arena: after the
+// M run on diagonal D ends at window position b with a hand-over to Ix / Iy, the gap cell is
+// position b of D itself; if that gap was opened right there, the path continues in M on the
+// diagonal one row up (Ix) or one column left (Iy) at the same position -- or, coming from a
+// neighbouring diagonal through the opposite gap, back on the main diagonal one position on.
+// Everything is warp-uniform except the window elements themselves.
+__device__ __forceinline__ void walk_step(Walk& w, const AlignArgs& a, int lane)
+{
+    if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
+    if (TAXI_TB_DIAGONALS != 3 || w.state != 0) { walk_run(w, a, lane, w.tb, w.ca, w.cb, w.valid); return; }
+    int D = 0, b = 0;   // diagonal (0 main, 1 one row up, 2 one column left) and position on it
+#pragma unroll 1
+    for (;;) {
+        const int src = min(b + lane, 31);
+        const bool inwin = b + lane < 32;
+        const int tbD = (D == 0) ? w.tb : (D == 1 ? w.tbU : w.tbL);
+        const int caD = (D == 1) ? w.caU : w.ca;
+        const int cbD = (D == 2) ? w.cbL : w.cb;
+        const bool vD = (D == 0) ? w.valid : (D == 1 ? w.validU : w.validL);
+        const int tb = __shfl_sync(TAXI_FULL_MASK, tbD, src);
+        const int ca = __shfl_sync(TAXI_FULL_MASK, caD, src);
+        const int cb = __shfl_sync(TAXI_FULL_MASK, cbD, src);
+        const bool valid = __shfl_sync(TAXI_FULL_MASK, (int)vD, src) != 0 && inwin;
+        const int i0 = w.i, j0 = w.j;
+        walk_run(w, a, lane, tb, ca, cb, valid);                     // the M run on diagonal D from position b
+        b += max(i0 - w.i, j0 - w.j);
+        if (w.state == 0 || b >= 32 || !(w.i > 0 && w.j > 0)) return;   // window exhausted, or the walk is over
+        // the gap cell: position b of diagonal D, entered in state w.state
+        const int g = w.state;
+        const int gtb = __shfl_sync(TAXI_FULL_MASK, tbD, b);
+        const int gca = __shfl_sync(TAXI_FULL_MASK, caD, b);
+        const int gcb = __shfl_sync(TAXI_FULL_MASK, cbD, b);
+        const bool gv = __shfl_sync(TAXI_FULL_MASK, (int)vD, b) != 0;
+        if (!gv) return;                                              // cannot happen while i, j > 0; stay safe
+        walk_run(w, a, lane, gtb, gca, gcb, lane == 0);               // one gap column
+        if (w.state != 0 || !(w.i > 0 && w.j > 0)) return;            // longer gap (or done): fetch a gap window
+        if (D == 0) D = g;                                            // Ix -> one row up, Iy -> one column left
+        else if (D != g) { D = 0; b += 1; }                           // opposite gap: back on the main diagonal
+        else return;                                                  // second gap the same way: not in the window
+        if (b >= 32) return;
+    }
 }
 
 __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lane)
@@ -188,6 +253,8 @@ __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, cons
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
     w.tb = w.ca = w.cb = 0; w.valid = false;
+    w.tbU = w.caU = 0; w.validU = false;
+    w.tbL = w.cbL = 0; w.validL = false;
     return w;
 }
 
@@ -198,8 +265,8 @@ __device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, cons
     while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
         walk_fetch<H>(wa, lane, trace, l0);
         walk_fetch<H>(wb, lane, trace, l0);
-        walk_advance(wa, a, lane);
-        walk_advance(wb, a, lane);
+        walk_step(wa, a, lane);
+        walk_step(wb, a, lane);
     }
     walk_finish(wa, a, lane);
     if (second) walk_finish(wb, a, lane);
