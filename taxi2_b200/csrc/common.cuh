@@ -32,6 +32,9 @@ struct Fast16 {
     int32_t neg;                       // "minus infinity" of the dead slots (multiple of 16, above every penalty)
     int32_t bias;                      // value representing transformed score 0 (multiple of 16), placed by the host so that
                                        // every reachable value of the padded DP fits the unsigned 16-bit window
+    uint32_t class_lut;                // nibble k = base_class of the symbol with code k (traceback counts work on codes)
+    uint32_t ascii_lo, ascii_hi;       // byte k = the symbol with code k (gapped strings are written from codes)
+    int32_t has_gap_symbol;            // '-' occurs inside the loaded sequences (input that was not normalized)
 };
 
 struct PairIndex { int xi, yi; long long out; };
@@ -73,7 +76,7 @@ __device__ __forceinline__ PairIndex pair_index(const AlignArgs& a, long long p)
 }
 
 // 0..3 = A,G,C,T (bit1 = pyrimidine: a transition flips only bit0); 4 = '-'; 5 = missing
-__device__ __forceinline__ int base_class(int c)
+__host__ __device__ __forceinline__ int base_class(int c)
 {
     const int u = c & 0xDF;  // fold ASCII case
     int k = 5;

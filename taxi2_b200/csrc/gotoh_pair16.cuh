@@ -66,177 +66,142 @@ template <int H> struct Pair16Geom {
     static constexpr int HB = (WORDS * 4 + 15) / 16 * 16;     // bytes per (lane, step)
 };
 
-// Warp-parallel first-path traceback over the 4-bit codes.  The walk is a chain of dependent
-// loads (each iteration needs the previous one's outcome), so (1) the walks of the two pairs a
-// warp has just aligned advance in lockstep -- both windows' loads are issued before either is
-// consumed -- and (2) in state M an iteration fetches the two neighbouring diagonals along with
-// the main one, so that isolated one-column gaps (the common case in barcode data) do not cost
-// two more round trips each (walk_step).  (Speculatively loading the next straight-ahead window
-// as well was measured: 2 % slower, the extra loads cost more than the latency they hide.)
+// Warp-parallel first-path traceback over the 4-bit codes.  An iteration looks at the next 32
+// cells the path would visit if it stayed in its state (diagonal for M, one row / one column for
+// Ix / Iy), follows it to the first cell that hands over to another state, and accounts for the
+// cells visited.  The walks of the two pairs a warp has just aligned advance in lockstep: both
+// windows' loads are issued before either is consumed.
+//
+// The walk is the only serial part of a pair and every one of its instructions competes with the
+// DP loops of the two other warps of the scheduler (skipping it is worth 10 %), so
+// it is written for instruction count: symbol codes and a class table instead of ASCII
+// classification, per-lane partial counts that are summed once at the end, window validity from
+// (i, j) instead of a ballot, and the gap-column bookkeeping reduced to what the state allows.
+// (Measured and dropped: fetching the two neighbouring diagonals so that one-column gaps stay in
+// one iteration -- 41 -> 25 iterations per 650 bp pair, same speed; prefetching the next
+// straight-ahead window -- 2 % slower.)
 struct Walk {
-    const uint8_t* x; const uint8_t* y;   // ASCII of the two sequences
+    const uint8_t* x; const uint8_t* y;   // symbol codes of the two sequences
     long long p;                          // pair index (outputs)
     int i, j, state;                      // current cell and state (0 = M, 1 = Ix, 2 = Iy)
     int half, off;                        // which 16-bit half of the arena; row -> slot offset
     int stride;                           // steps per stripe in the arena (multi-stripe kernel)
-    int same, ts, tv, gapc, pend;
+    int n, same, ts;                      // per-lane partial counts (both-real, identical, transitions)
+    int gapc, pend;                       // warp-uniform: gap columns inside / after the both-real span so far
     bool seen;
     int64_t wpos;                         // write cursor of the gapped strings
     int score;
-    // the window elements this lane holds.  In state M three diagonals are fetched at once:
-    // lane k has the cells (i-k, j-k) [main], (i-k-1, j-k) [one row up] and (i-k, j-k-1) [one
-    // column left], so that a one-column gap does not end the iteration (see walk_step)
-    int tb, ca, cb; bool valid;
-    int tbU, caU; bool validU;            // (i-k-1, j-k): x[i-k-2]; its y character is cb
-    int tbL, cbL; bool validL;            // (i-k, j-k-1): y[j-k-2]; its x character is ca
+    int tb, ca, cb;                       // the window element this lane holds: traceback code, x / y symbol codes
 };
 
-#ifndef TAXI_TB_DIAGONALS
-#define TAXI_TB_DIAGONALS 3
-#endif
-
-template <int H>
-__device__ __forceinline__ int trace_code(const Walk& w, const uint8_t* trace, int l0, int ii, int jj)
+// address of the traceback code of cell (ii, jj); MULTI = arena with several stripes
+template <int H, bool MULTI>
+__device__ __forceinline__ const uint8_t* trace_addr(const Walk& w, const uint8_t* trace, int l0, int ii, int jj)
 {
     constexpr int HB = Pair16Geom<H>::HB;
     const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
-    const int st = slot / (32 * H), q = slot % (32 * H);   // stripe (0 for the single-stripe kernels)
+    int st = 0, q = slot;
+    if (MULTI) { st = slot / (32 * H); q = slot % (32 * H); }
     const int l = q / H, r = q % H;
     const int first = (st == 0) ? l0 : 0;                  // only the first stripe starts at a later lane
-    return (int)__ldcg(trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half);
+    return trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half;
 }
 
-template <int H>
+template <int H, bool MULTI>
 __device__ __forceinline__ void walk_fetch(Walk& w, int lane, const uint8_t* trace, int l0)
 {
     const int di = (w.state != 2), dj = (w.state != 1);
     const int ii = w.i - lane * di, jj = w.j - lane * dj;
-    w.valid = w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1;
     w.tb = 0; w.ca = 0; w.cb = 0;
-    w.tbU = w.caU = 0; w.validU = false;
-    w.tbL = w.cbL = 0; w.validL = false;
-    if (w.valid) {
-        w.tb = trace_code<H>(w, trace, l0, ii, jj);
+    if (w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1) {
+        w.tb = (int)__ldcg(trace_addr<H, MULTI>(w, trace, l0, ii, jj));
         w.ca = (int)__ldg(w.x + ii - 1);
         w.cb = (int)__ldg(w.y + jj - 1);
-        if (TAXI_TB_DIAGONALS == 3 && w.state == 0) {
-            w.validU = ii >= 2;
-            w.validL = jj >= 2;
-            if (w.validU) { w.tbU = trace_code<H>(w, trace, l0, ii - 1, jj); w.caU = (int)__ldg(w.x + ii - 2); }
-            if (w.validL) { w.tbL = trace_code<H>(w, trace, l0, ii, jj - 1); w.cbL = (int)__ldg(w.y + jj - 2); }
-        }
     }
 }
 
-// Follow the path through one window: lane m holds the m-th cell the path would visit if it stayed
-// in w.state; the run ends at the first cell that hands over to another state (or at the window's
-// last valid cell).  Counts, strings and (i, j, state) are updated for the cells visited.
-__device__ __forceinline__ void walk_run(Walk& w, const AlignArgs& a, int lane, int tb, int ca, int cb, bool valid)
+__device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int lane)
 {
-    const int state = w.state;
+    if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
+    const int state = w.state, tb = w.tb;
     const int di = (state != 2), dj = (state != 1);
+    // cells of the window that exist: a prefix of the lanes
+    const int nvalid = min(32, min(di ? w.i : 32, dj ? w.j : 32));
     // state I would hand over to if the path reaches my cell in `state`
     int ns;
     if (state == 0) ns = 3 - (tb & 3);            // 3 -> M, 2 -> Ix, 1 -> Iy
     else if (state == 1) ns = (tb & 4) ? 0 : 1;   // Ix: opened from M, or extended
     else ns = (tb & 8) ? 0 : 2;                   // Iy
-    const unsigned cont = __ballot_sync(TAXI_FULL_MASK, valid && ns == state);
-    const unsigned vmask = __ballot_sync(TAXI_FULL_MASK, valid);
-    const int f = __ffs(~cont) - 1;
-    int V = (f < 0) ? 32 : f + 1;
-    V = min(V, __popc(vmask));
-    const unsigned visited = (V == 32) ? 0xffffffffu : ((1u << V) - 1u);
+    const unsigned cont = __ballot_sync(TAXI_FULL_MASK, ns == state);
+    const int V = min(__ffs(~cont | 0x80000000u), nvalid);   // cells visited: up to and including the first hand-over
     const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
-    const int ka = (state == 2) ? 4 : base_class(ca);
-    const int kb = (state == 1) ? 4 : base_class(cb);
-    const bool both = ka < 4 && kb < 4;
-    const int d = ka ^ kb;
-    const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
-    const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
-    const unsigned tsm = __ballot_sync(TAXI_FULL_MASK, both && d == 1) & visited;
-    const unsigned tvm = __ballot_sync(TAXI_FULL_MASK, both && d > 1) & visited;
-    if (bm) {
-        w.ts += __popc(tsm); w.tv += __popc(tvm); w.same += __popc(bm & ~(tsm | tvm));
-        const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
-        const unsigned below = (1u << fb) - 1u;
-        const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
-        if (w.seen) w.gapc += w.pend + __popc(gm & below);
-        w.gapc += __popc(gm & upto & ~below);
-        w.pend = __popc(gm & ~upto);
-        w.seen = true;
+    const bool mine = lane < V;
+    const unsigned visited = 0xffffffffu >> (32 - V);
+    const uint32_t lut = a.f16.class_lut;
+    if (state == 0) {
+        const int ka = (int)((lut >> (4 * w.ca)) & 7u), kb = (int)((lut >> (4 * w.cb)) & 7u);
+        const bool both = (ka | kb) < 4;
+        const int d = ka ^ kb;
+        w.n += (mine && both);
+        w.same += (mine && both && d == 0);
+        w.ts += (mine && both && d == 1);
+        const unsigned bm = __ballot_sync(TAXI_FULL_MASK, both) & visited;
+        if (!a.f16.has_gap_symbol) {   // aligned columns hold no gap: only the both-real span moves
+            if (bm) { w.gapc += w.seen ? w.pend : 0; w.pend = 0; w.seen = true; }
+        } else {                       // '-' inside a sequence: a column of '-' against a base counts as a gap column
+            const unsigned gm = __ballot_sync(TAXI_FULL_MASK, (ka == 4) != (kb == 4) && (ka < 4 || kb < 4)) & visited;
+            if (bm) {
+                const int fb = __ffs(bm) - 1, lb = 31 - __clz(bm);
+                const unsigned below = (1u << fb) - 1u;
+                const unsigned upto = (lb == 31) ? 0xffffffffu : ((2u << lb) - 1u);
+                if (w.seen) w.gapc += w.pend + __popc(gm & below);
+                w.gapc += __popc(gm & upto & ~below);
+                w.pend = __popc(gm & ~upto);
+                w.seen = true;
+            } else {
+                w.pend += __popc(gm);
+            }
+        }
     } else {
-        w.pend += __popc(gm);
+        // a gap run: every column whose symbol is a base is a gap column, pending until the next both-real column
+        const int k = (int)((lut >> (4 * (state == 1 ? w.ca : w.cb))) & 7u);
+        w.pend += __popc(__ballot_sync(TAXI_FULL_MASK, k < 4) & visited);
     }
-    if (a.aln_x != nullptr && lane < V) {
-        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
-        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
+    if (a.aln_x != nullptr && mine) {
+        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, w.ca);
+        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, w.cb);
     }
     w.wpos -= V;
     w.i -= V * di; w.j -= V * dj;
     w.state = next;
 }
 
-// One iteration on the data walk_fetch brought in.  In a gap state, or with single-diagonal
-// windows, that is one run.  In state M with the two neighbouring diagonals at hand the walk goes
-// on through one-column gaps without another (dependent, ~1 us) round trip to the arena: after the
-// M run on diagonal D ends at window position b with a hand-over to Ix / Iy, the gap cell is
-// position b of D itself; if that gap was opened right there, the path continues in M on the
-// diagonal one row up (Ix) or one column left (Iy) at the same position -- or, coming from a
-// neighbouring diagonal through the opposite gap, back on the main diagonal one position on.
-// Everything is warp-uniform except the window elements themselves.
-__device__ __forceinline__ void walk_step(Walk& w, const AlignArgs& a, int lane)
-{
-    if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
-    if (TAXI_TB_DIAGONALS != 3 || w.state != 0) { walk_run(w, a, lane, w.tb, w.ca, w.cb, w.valid); return; }
-    int D = 0, b = 0;   // diagonal (0 main, 1 one row up, 2 one column left) and position on it
-#pragma unroll 1
-    for (;;) {
-        const int src = min(b + lane, 31);
-        const bool inwin = b + lane < 32;
-        const int tbD = (D == 0) ? w.tb : (D == 1 ? w.tbU : w.tbL);
-        const int caD = (D == 1) ? w.caU : w.ca;
-        const int cbD = (D == 2) ? w.cbL : w.cb;
-        const bool vD = (D == 0) ? w.valid : (D == 1 ? w.validU : w.validL);
-        const int tb = __shfl_sync(TAXI_FULL_MASK, tbD, src);
-        const int ca = __shfl_sync(TAXI_FULL_MASK, caD, src);
-        const int cb = __shfl_sync(TAXI_FULL_MASK, cbD, src);
-        const bool valid = __shfl_sync(TAXI_FULL_MASK, (int)vD, src) != 0 && inwin;
-        const int i0 = w.i, j0 = w.j;
-        walk_run(w, a, lane, tb, ca, cb, valid);                     // the M run on diagonal D from position b
-        b += max(i0 - w.i, j0 - w.j);
-        if (w.state == 0 || b >= 32 || !(w.i > 0 && w.j > 0)) return;   // window exhausted, or the walk is over
-        // the gap cell: position b of diagonal D, entered in state w.state
-        const int g = w.state;
-        const int gtb = __shfl_sync(TAXI_FULL_MASK, tbD, b);
-        const int gca = __shfl_sync(TAXI_FULL_MASK, caD, b);
-        const int gcb = __shfl_sync(TAXI_FULL_MASK, cbD, b);
-        const bool gv = __shfl_sync(TAXI_FULL_MASK, (int)vD, b) != 0;
-        if (!gv) return;                                              // cannot happen while i, j > 0; stay safe
-        walk_run(w, a, lane, gtb, gca, gcb, lane == 0);               // one gap column
-        if (w.state != 0 || !(w.i > 0 && w.j > 0)) return;            // longer gap (or done): fetch a gap window
-        if (D == 0) D = g;                                            // Ix -> one row up, Iy -> one column left
-        else if (D != g) { D = 0; b += 1; }                           // opposite gap: back on the main diagonal
-        else return;                                                  // second gap the same way: not in the window
-        if (b >= 32) return;
-    }
-}
-
 __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lane)
 {
     if (a.aln_x != nullptr) {
         // leading end gap: whatever is left of x (vertical) or y (horizontal)
-        for (int k = lane; k < w.i; k += 32) { a.aln_x[w.wpos - 1 - k] = __ldg(w.x + w.i - 1 - k); a.aln_y[w.wpos - 1 - k] = '-'; }
+        for (int k = lane; k < w.i; k += 32) {
+            a.aln_x[w.wpos - 1 - k] = (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, (int)__ldg(w.x + w.i - 1 - k));
+            a.aln_y[w.wpos - 1 - k] = '-';
+        }
         w.wpos -= w.i;
-        for (int k = lane; k < w.j; k += 32) { a.aln_x[w.wpos - 1 - k] = '-'; a.aln_y[w.wpos - 1 - k] = __ldg(w.y + w.j - 1 - k); }
+        for (int k = lane; k < w.j; k += 32) {
+            a.aln_x[w.wpos - 1 - k] = '-';
+            a.aln_y[w.wpos - 1 - k] = (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, (int)__ldg(w.y + w.j - 1 - k));
+        }
         w.wpos -= w.j;
         if (lane == 0) a.aln_start[w.p] = w.wpos;
     }
+    const int n = (int)__reduce_add_sync(TAXI_FULL_MASK, (unsigned)w.n);
+    const int same = (int)__reduce_add_sync(TAXI_FULL_MASK, (unsigned)w.same);
+    const int ts = (int)__reduce_add_sync(TAXI_FULL_MASK, (unsigned)w.ts);
+    const int tv = n - same - ts;
     if (lane != 0) return;
     if (a.score) a.score[w.p] = w.score;
-    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * w.p) = make_int4(w.same, w.ts, w.tv, w.gapc);
+    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * w.p) = make_int4(same, ts, tv, w.gapc);
     if (a.metrics) {
         double m[4];
-        metrics_from_counts(w.same, w.ts, w.tv, w.gapc, m);
+        metrics_from_counts(same, ts, tv, w.gapc, m);
         double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * w.p);
         dst[0] = make_double2(m[0], m[1]);
         dst[1] = make_double2(m[2], m[3]);
@@ -249,32 +214,29 @@ __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, cons
     Walk w;
     w.x = x; w.y = y; w.p = p; w.i = nA; w.j = nB; w.state = 3 - (int)(fin & 3u);
     w.half = half; w.off = off; w.stride = stride;
-    w.same = w.ts = w.tv = w.gapc = w.pend = 0; w.seen = false;
+    w.n = w.same = w.ts = w.gapc = w.pend = 0; w.seen = false;
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
-    w.tb = w.ca = w.cb = 0; w.valid = false;
-    w.tbU = w.caU = 0; w.validU = false;
-    w.tbL = w.cbL = 0; w.validL = false;
+    w.tb = w.ca = w.cb = 0;
     return w;
 }
 
-template <int H>
+template <int H, bool MULTI>
 __device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, const uint8_t* trace, int l0, Walk& wa, Walk& wb, bool second)
 {
     if (!second) { wb.i = 0; wb.j = 0; }
     while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
-        walk_fetch<H>(wa, lane, trace, l0);
-        walk_fetch<H>(wb, lane, trace, l0);
-        walk_step(wa, a, lane);
-        walk_step(wb, a, lane);
+        walk_fetch<H, MULTI>(wa, lane, trace, l0);
+        walk_fetch<H, MULTI>(wb, lane, trace, l0);
+        walk_advance(wa, a, lane);
+        walk_advance(wb, a, lane);
     }
     walk_finish(wa, a, lane);
     if (second) walk_finish(wb, a, lane);
 }
 
 struct PairRef {
-    const uint8_t* xb; const uint8_t* yb;   // ASCII (traceback classification / strings)
-    const uint8_t* xc; const uint8_t* yc;   // 3-bit codes (DP)
+    const uint8_t* xc; const uint8_t* yc;   // 3-bit codes (DP, traceback counts, gapped strings via Fast16::ascii_*)
     int nA, nB;
     long long out;                          // index of this pair's results
 };
@@ -286,7 +248,7 @@ __device__ __forceinline__ PairRef pair_ref(const AlignArgs& a, long long p)
     const int64_t xo = a.xoff[xi], yo = a.yoff[yi];
     PairRef r;
     r.out = pi.out;
-    r.xb = a.xb + xo; r.yb = a.yb + yo; r.xc = a.xc + xo; r.yc = a.yc + yo;
+    r.xc = a.xc + xo; r.yc = a.yc + yo;
     r.nA = (int)(a.xoff[xi + 1] - xo);
     r.nB = (int)(a.yoff[yi + 1] - yo);
     return r;
@@ -405,9 +367,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
     finB = __shfl_sync(TAXI_FULL_MASK, finB, llB);
     __syncwarp();
 
-    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, 0, finA, f.beta, f.bias);
-    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, 0, finB, f.beta, f.bias);
-    traceback_two<H>(a, lane, trace, 0, wa, wb, p1 != p0);
+    Walk wa = walk_start(a, A.out, A.xc, A.yc, A.nA, A.nB, 0, 0, finA, f.beta, f.bias);
+    Walk wb = walk_start(a, B.out, B.xc, B.yc, B.nA, B.nB, 1, 0, finB, f.beta, f.bias);
+    traceback_two<H, false>(a, lane, trace, 0, wa, wb, p1 != p0);
 }
 
 // Bottom-aligned variant: the rows of each pair are shifted (per half) so that row nA always sits
@@ -535,9 +497,9 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta, f.bias);
-    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta, f.bias);
-    traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
+    Walk wa = walk_start(a, A.out, A.xc, A.yc, A.nA, A.nB, 0, offA, finA, f.beta, f.bias);
+    Walk wb = walk_start(a, B.out, B.xc, B.yc, B.nA, B.nB, 1, offB, finB, f.beta, f.bias);
+    traceback_two<H, false>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 
 // Multi-stripe form of the bottom-aligned variant for x longer than 32*H - 1: the slots are cut
@@ -669,9 +631,9 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
     finB = __shfl_sync(TAXI_FULL_MASK, finB, 31);
     __syncwarp();
 
-    Walk wa = walk_start(a, A.out, A.xb, A.yb, A.nA, A.nB, 0, offA, finA, f.beta, f.bias, stride);
-    Walk wb = walk_start(a, B.out, B.xb, B.yb, B.nA, B.nB, 1, offB, finB, f.beta, f.bias, stride);
-    traceback_two<H>(a, lane, trace, l0, wa, wb, p1 != p0);
+    Walk wa = walk_start(a, A.out, A.xc, A.yc, A.nA, A.nB, 0, offA, finA, f.beta, f.bias, stride);
+    Walk wb = walk_start(a, B.out, B.xc, B.yc, B.nA, B.nB, 1, offB, finB, f.beta, f.bias, stride);
+    traceback_two<H, true>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 
 #ifndef PAIR16_WPB

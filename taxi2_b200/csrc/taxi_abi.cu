@@ -232,6 +232,15 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     Fast16 f;
     f.D16 = 16 * D; f.beta = beta;
     f.tlo = (uint32_t)f.D16 * 0x01010100u; f.thi = (uint32_t)f.D16 * 0x01010101u;
+    f.class_lut = 0x55555555u; f.ascii_lo = f.ascii_hi = 0; f.has_gap_symbol = 0;
+    for (int ch = 0; ch < 256; ++ch) {
+        const int k = c->codebook[ch];
+        if (k < 0 || k > 6) continue;
+        f.class_lut = (f.class_lut & ~(0xFu << (4 * k))) | ((uint32_t)base_class(ch) << (4 * k));
+        if (k < 4) f.ascii_lo |= (uint32_t)ch << (8 * k);
+        else f.ascii_hi |= (uint32_t)ch << (8 * (k - 4));
+        if (ch == '-') f.has_gap_symbol = 1;
+    }
     f.PoX = 16 * (match - io); f.PeX = 16 * (match - ie); f.PeoX = 16 * (match - eo); f.PeeX = 16 * (match - ee);
     f.PoY = -16 * io; f.PeY = -16 * ie; f.PeoY = -16 * eo; f.PeeY = -16 * ee;
     // Range.  The best transformed value is 0 (all matches), so the bias sits at the top of the
