@@ -1,7 +1,8 @@
 """Partitions (individual id -> subset) as far as the distance tasks need them.
 
-Mirrors /root/reference/src/itaxotools/taxi2/partitions.py:15-110 for the tabular formats; the
-Spart / Fasta / Excel partition readers are out of scope (metadata join, not on the compute path).
+Mirrors /root/reference/src/itaxotools/taxi2/partitions.py:15-110 for the tabular formats and
+:127-155 for FASTA titles ("individual|subset"); the Spart / Excel partition readers are out of
+scope (third-party parsers, not on the compute path).
 """
 from __future__ import annotations
 
@@ -10,6 +11,7 @@ from pathlib import Path
 from typing import Callable, Literal, NamedTuple
 
 from .handlers import FileHandler, ReadHandle, WriteHandle
+from .sequences import _fasta_records
 
 
 class Classification(NamedTuple):
@@ -81,3 +83,35 @@ class Tabular(PartitionHandler):
 
 class Tabfile(Tabular, PartitionHandler):
     subhandler = FileHandler.Tabular.Tabfile
+
+
+class Fasta(PartitionHandler):
+    """Subsets from FASTA titles `>individual<separator>subset`; titles without the separator are
+    reported and skipped (partitions.py:127-137)."""
+
+    def _iter_read_inner(self, separator: str = "|") -> ReadHandle[Classification]:
+        with open(self.path, "r") as handle:
+            yield self
+            for title, _ in _fasta_records(handle):
+                individual, found, subset = title.partition(separator)
+                if not found:
+                    print(f"Could not extract partition info from fasta line: {title}")
+                    continue
+                yield Classification(individual, subset)
+
+    @classmethod
+    def has_subsets(cls, path: Path, separator: str = "|") -> bool:
+        if not separator:
+            return False
+        with open(path, "r") as handle:
+            for title, _ in _fasta_records(handle):
+                return separator in title
+
+    @classmethod
+    def guess_subset_separator(cls, path: Path) -> str | None:
+        with open(path, "r") as handle:
+            for title, _ in _fasta_records(handle):
+                for separator in "|.":
+                    if separator in title:
+                        return separator
+            return None

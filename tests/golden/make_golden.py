@@ -13,6 +13,7 @@ Sources (relative to /root/reference):
   tests/test_statistics.py:113-250    -> statistics_cases.json (17 count + 108 statistic vectors)
   tests/test_statistics/*             -> statistics/ (writer fixtures)
   samples/Taxi2test1_ca200.tab        -> un-aligned 200-row resample for the align=False parity run
+  tests/test_partitions/*.{tsv,fas}, tests/test_handlers/*.tsv -> partitions/, handlers/ (reader fixtures)
 
 The reference test modules cannot be imported here (Bio / itaxotools.* are absent), so the
 tables are read with `ast` instead of being executed.
@@ -105,6 +106,15 @@ def statistics_cases():
     return out
 
 
+def reader_fixtures():
+    """Input-path fixtures: partition files (tabular + FASTA titles) and plain tab files."""
+    for sub, pattern in (("partitions", ("*.tsv", "*.fas")), ("handlers", ("*.tsv",))):
+        (OUT / sub).mkdir(exist_ok=True)
+        for pat in pattern:
+            for path in sorted((REF / "tests" / f"test_{sub}").glob(pat)):
+                shutil.copyfile(path, OUT / sub / path.name)
+
+
 def samples():
     for name in ("Taxi2test1_10", "Taxi2test1_50", "Taxi2test1_120", "Taxi2test1_ca200"):
         shutil.copyfile(REF / "samples" / f"{name}.tab", OUT / f"{name}.tab")
@@ -118,4 +128,5 @@ if __name__ == "__main__":
     (OUT / "statistics_cases.json").write_text(json.dumps(statistics_cases(), indent=1) + "\n")
     samples()
     handler_fixtures()
+    reader_fixtures()
     print("golden fixtures written to", OUT)
