@@ -49,15 +49,22 @@ class DistanceMetric(Type):
     def _is_number(x) -> bool:
         return not (x is None or isnan(x) or isinf(x))
 
+    # the four metrics of the pair seen last: every caller asks for them back to back on the same
+    # two strings (versus_all.py:546-552 and siblings), and one device call yields all four
+    _last_pair: tuple | None = None
+    _last_values = None
+
     def _calculate(self, x: str, y: str) -> float | None:
         if self.column is None:
             raise NotImplementedError()
-        from .engine import default_engine
+        if DistanceMetric._last_pair != (x, y):
+            from .engine import default_engine
 
-        eng = default_engine()
-        eng.load([x], 0)
-        eng.load([y], 1)
-        value = float(eng.count_pairs([0], [0], want=("metrics",))["metrics"][0, self.column])
+            eng = default_engine()
+            eng.load([x, y], 0)
+            DistanceMetric._last_values = eng.count_pairs([0], [1], want=("metrics",))["metrics"][0].copy()
+            DistanceMetric._last_pair = (x, y)
+        value = float(DistanceMetric._last_values[self.column])
         return value if self._is_number(value) else None
 
     def calculate(self, x: Sequence, y: Sequence) -> Distance:
