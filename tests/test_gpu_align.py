@@ -168,6 +168,19 @@ def test_multi_stripe_long_pairs(engine):
     assert_kernel(engine, xs, ys, (1, -1, -8, -1, -1, -1), 18)
 
 
+def test_very_long_and_very_lopsided_pairs(engine):
+    """The general kernel far beyond the packed kernel's window: a 12 000 x 9 000 bp pair (18
+    stripes), a 1 bp sequence against 7 000 bp and the reverse, under Gotoh and NW score sets."""
+    rng = np.random.default_rng(12000)
+    xs, ys = random_pairs(rng, 1, 11800, 12000, sub=0.08, indel=0.01)
+    ys = [ys[0][:9000]]
+    long7k = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 7000))
+    xs += [b"G", long7k]
+    ys += [long7k, b"T"]
+    for scores in [(1, -1, -8, -1, -1, -1), (2, -3, -4, -4, -4, -4)]:
+        check_pairs(engine, xs, ys, scores, strings=True, expect_fast=False)
+
+
 def assert_kernel(engine, xs, ys, scores, kernel):
     engine.set_scores(scores)
     engine.load(xs, 0)
