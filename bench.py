@@ -219,7 +219,11 @@ def main() -> None:
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's version / debug lines go to stderr
+        # stdout carries exactly one JSON line.  This image exports NCCL_DEBUG=VERSION, whose only
+        # effect is a "NCCL version ..." line on stdout (NCCL_DEBUG_FILE does not move that one);
+        # any other level the caller asked for is kept, with its output sent to stderr.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
