@@ -199,7 +199,8 @@ class Engine:
 
     @property
     def last_kernel(self) -> int:
-        """32 = general int32 kernel, 16 = packed 16-bit two-pairs-per-warp kernel."""
+        """32 = general int32 kernel; 16 / 17 / 18 = packed 16-bit kernel (top-aligned / bottom-aligned /
+        bottom-aligned in several stripes); 48 = a rectangle whose rows were split into several launches."""
         return int(self._lib.taxi_last_kernel(self._ctx))
 
     def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None) -> dict:
