@@ -76,6 +76,8 @@ int taxi_align_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_
 /*
  * Same for the rectangle [x0, x0+nx) x [y0, y0+ny) of SequencePairs.fromProduct (pairs.py:23-25),
  * row-major: pair p = (x0 + p / ny, y0 + p % ny).  Outputs are host buffers of nx*ny entries.
+ * Any size: the rectangle is walked in blocks of whole rows (at most 2^24 pairs of device-side
+ * results at a time), each block downloaded into its place.
  */
 int taxi_align_rect(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
                     int32_t* out_score, int32_t* out_counts, double* out_metrics);

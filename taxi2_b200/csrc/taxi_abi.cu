@@ -699,6 +699,11 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     return enqueue_align(c, a, mr, mc);
 }
 
+// Host-facing rectangles of any size: the device-side result buffers hold at most kChunkPairs
+// pairs, so a large rectangle (BASELINE C3 is 2.5e9 ordered pairs = 120 GB of results) is walked
+// in blocks of whole rows, each downloaded into its place of the caller's arrays.
+constexpr long long kChunkPairs = 1LL << 24;
+
 int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
                     int32_t* out_score, int32_t* out_counts, double* out_metrics)
 {
@@ -709,10 +714,17 @@ int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     if (npairs == 0) return TAXI_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    if ((rc = reserve_outputs(c, npairs, flags))) return rc;
-    if ((rc = taxi_align_rect_device(c, x0, nx, y0, ny, flags, c->d_score.p, c->d_counts.p, c->d_metrics.p))) return rc;
-    if ((rc = download_outputs(c, npairs, flags, out_score, out_counts, out_metrics))) return rc;
-    return finish_align(c);
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
+    for (int32_t r0 = 0; r0 < nx; r0 += rows) {
+        const int32_t nr = std::min(rows, nx - r0);
+        const long long at = (long long)r0 * ny, n = (long long)nr * ny;
+        if ((rc = taxi_align_rect_device(c, x0 + r0, nr, y0, ny, flags, c->d_score.p, c->d_counts.p, c->d_metrics.p))) return rc;
+        if ((rc = download_outputs(c, n, flags, out_score ? out_score + at : nullptr, out_counts ? out_counts + 4 * at : nullptr,
+                                   out_metrics ? out_metrics + 4 * at : nullptr))) return rc;
+        if ((rc = finish_align(c))) return rc;
+    }
+    return TAXI_OK;
 }
 
 int taxi_align_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,
@@ -846,10 +858,18 @@ int taxi_count_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    if ((rc = reserve_outputs(c, npairs, flags & ~TAXI_OUT_SCORE))) return rc;
-    if ((rc = taxi_count_rect_device(c, x0, nx, y0, ny, flags, c->d_counts.p, c->d_metrics.p))) return rc;
-    if ((rc = download_outputs(c, npairs, flags & ~TAXI_OUT_SCORE, nullptr, out_counts, out_metrics))) return rc;
-    return finish_align(c);
+    flags &= ~(uint32_t)TAXI_OUT_SCORE;
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
+    for (int32_t r0 = 0; r0 < nx; r0 += rows) {
+        const int32_t nr = std::min(rows, nx - r0);
+        const long long at = (long long)r0 * ny, n = (long long)nr * ny;
+        if ((rc = taxi_count_rect_device(c, x0 + r0, nr, y0, ny, flags, c->d_counts.p, c->d_metrics.p))) return rc;
+        if ((rc = download_outputs(c, n, flags, nullptr, out_counts ? out_counts + 4 * at : nullptr,
+                                   out_metrics ? out_metrics + 4 * at : nullptr))) return rc;
+        if ((rc = finish_align(c))) return rc;
+    }
+    return TAXI_OK;
 }
 
 int taxi_count_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs, uint32_t flags,

@@ -395,3 +395,30 @@ def test_extreme_but_eligible_scores(engine):
         check_pairs(engine, xs, ys, scores, strings=False, expect_fast=False)
     xs, ys = random_pairs(rng, 120, 1, 60, sub=0.2, indel=0.05)
     check_pairs(engine, xs, ys, (7, 0, -60, -9, -30, -9), expect_fast=True)   # same scores fit at 60 bp
+
+
+def test_host_rectangle_larger_than_one_device_block(engine):
+    """taxi_align_rect / taxi_count_rect walk a rectangle of more than 2^24 pairs in blocks of whole
+    rows (the device result buffers are bounded); every block must land in its place."""
+    rng = np.random.default_rng(224)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    xs = [al[rng.integers(0, 4, int(rng.integers(20, 41)))].tobytes() for _ in range(5000)]
+    ys = [al[rng.integers(0, 4, int(rng.integers(20, 41)))].tobytes() for _ in range(3400)]   # 1.7e7 pairs > 2^24
+    engine.set_scores(None)
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    big = engine.align_rect(0, len(xs), 0, len(ys), want=("score", "counts"))
+    assert engine.stats()["launches"] >= 2
+    for x0 in (0, 4930, 4934, 4999):           # first block, the rows around the block boundary, the last row
+        part = engine.align_rect(x0, 1, 0, len(ys), want=("score", "counts"))
+        assert np.array_equal(big["score"][x0], part["score"][0])
+        assert np.array_equal(big["counts"][x0], part["counts"][0])
+    rows = rng.integers(0, len(xs), 40)
+    cols = rng.integers(0, len(ys), 40)
+    want = oracle_batch(xs, ys, rows.astype(np.int32), cols.astype(np.int32), None)
+    assert np.array_equal(big["score"][rows, cols], want["score"])
+    assert np.array_equal(big["counts"][rows, cols], want["counts"])
+    free = engine.count_rect(0, len(xs), 0, len(ys), want=("counts",))
+    for k in range(40):
+        c = oracle.count(xs[rows[k]].decode(), ys[cols[k]].decode()) or (0, 0, 0, 0)
+        assert tuple(free["counts"][rows[k], cols[k]]) == tuple(c)
