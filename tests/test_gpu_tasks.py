@@ -63,6 +63,20 @@ def test_versus_all_outputs(tmp_path, align, write, multiply, native):
     assert_same_tree(task.work_dir, want)
 
 
+def test_versus_all_on_the_50_sequence_sample(tmp_path):
+    """The reference's Taxi2test1_50.tab as shipped (2 500 ordered pairs, 416-618 bp, species and
+    genera from the organism column): all output files, aligned pairs included, byte for byte."""
+    seqs, species, genera = load("Taxi2test1_50.tab")
+    task = VersusAll()
+    task.work_dir = tmp_path / "got"
+    task.progress_handler = SILENT
+    task.input.sequences = seqs
+    task.input.species, task.input.genera = species, genera
+    task.start()
+    ref_pipeline.versus_all(list(seqs), tmp_path / "want", species, genera)
+    assert_same_tree(task.work_dir, tmp_path / "want")
+
+
 @pytest.mark.parametrize("fmt", ["{:.4f}", "{:.2e}", "{:>9.3f}"])
 def test_versus_all_without_partitions_and_metric_subset(tmp_path, fmt):
     seqs, _, _ = load("Taxi2test1_10.tab")
