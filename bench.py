@@ -278,14 +278,24 @@ def main() -> None:
     checksum = int(d_counts.sum().item())
 
     # ---- end to end through the C ABI with host buffers ("e2e") --------------------------------
+    from taxi2_b200.engine import PinnedArray
+
     eng2 = Engine(local_rank)
     h2d = d2h = 0
+    # inputs sit in page-locked host memory: the sequence bytes as a whole, the per-tile offsets
+    # in two small pinned scratch arrays that are rewritten every step
+    pinned_data = PinnedArray(data.shape, np.uint8)
+    pinned_data.array[:] = data
+    pinned_xoff = PinnedArray((TILE_X + 1,), np.int64)
+    pinned_yoff = PinnedArray((TILE_Y + 1,), np.int64)
 
     def step_e2e(k: int) -> None:
         nonlocal h2d, d2h
         x0, y0 = tile_of(k, rank, world, n)
-        xs = (data[off[x0]:off[x0 + TILE_X]], off[x0:x0 + TILE_X + 1] - off[x0])
-        ys = (data[off[y0]:off[y0 + TILE_Y]], off[y0:y0 + TILE_Y + 1] - off[y0])
+        np.subtract(off[x0:x0 + TILE_X + 1], off[x0], out=pinned_xoff.array)
+        np.subtract(off[y0:y0 + TILE_Y + 1], off[y0], out=pinned_yoff.array)
+        xs = (pinned_data.array[off[x0]:off[x0 + TILE_X]], pinned_xoff.array)
+        ys = (pinned_data.array[off[y0]:off[y0 + TILE_Y]], pinned_yoff.array)
         ta = time.perf_counter()
         eng2.load(xs, 0)
         eng2.load(ys, 1)
