@@ -59,6 +59,7 @@ struct CountArgs {
     Planes x, y;
     const int32_t* px; const int32_t* py;   // explicit list or nullptr (rect)
     int32_t x0, y0, nx, ny;
+    int32_t slab;                           // rect mode: x rows staged in shared memory per block (<= COUNT_SLAB)
     long long npairs;
     int32_t* counts;   // [npairs][4] or nullptr
     double* metrics;   // [npairs][4] or nullptr
@@ -109,15 +110,15 @@ struct CountState {
 // from shared memory as warp broadcasts.  Results are written coalesced, 16 B + 32 B per pair.
 constexpr int COUNT_TY = 256;
 constexpr int COUNT_RX = 8;
-constexpr int COUNT_SLAB = 64;   // x rows staged in shared memory per block
+constexpr int COUNT_SLAB = 64;   // x rows staged in shared memory per block (fewer when the sequences are long)
 
 __global__ void __launch_bounds__(COUNT_TY, 2) count_rect_kernel(const CountArgs a)
 {
-    extern __shared__ uint32_t xs[];   // [COUNT_SLAB][4][W]
+    extern __shared__ uint32_t xs[];   // [slab][4][W]
     const int W = min(a.x.W, a.y.W);
     const int yj = blockIdx.x * COUNT_TY + threadIdx.x;          // column inside the rectangle
-    const int xbase = blockIdx.y * COUNT_SLAB;                   // first row of the slab
-    const int rows = min(COUNT_SLAB, a.nx - xbase);
+    const int xbase = blockIdx.y * a.slab;                       // first row of the slab
+    const int rows = min(a.slab, a.nx - xbase);
     for (int k = threadIdx.x; k < rows * 4 * W; k += COUNT_TY) {
         const int r = k / (4 * W), pw = k % (4 * W);
         xs[k] = a.x.at(pw / W, pw % W, a.x0 + xbase + r);

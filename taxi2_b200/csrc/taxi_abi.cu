@@ -819,10 +819,13 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
         count_pairs_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
     } else {
         const int W = std::min(X.W, Y.W);
-        const size_t smem = (size_t)COUNT_SLAB * 4 * W * sizeof(uint32_t);
-        if (smem > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
+        // x rows per block: as many as fit ~96 KB of shared memory (two blocks per SM), at most COUNT_SLAB
+        const size_t row_bytes = (size_t)4 * W * sizeof(uint32_t);
+        if (row_bytes > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
+        a.slab = (int32_t)std::max<size_t>(1, std::min<size_t>(COUNT_SLAB, (96 * 1024) / row_bytes));
+        const size_t smem = (size_t)a.slab * row_bytes;
         CUDA_TRY(cudaFuncSetAttribute(count_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)((a.ny + COUNT_TY - 1) / COUNT_TY), (unsigned)((a.nx + COUNT_SLAB - 1) / COUNT_SLAB));
+        dim3 grid((unsigned)((a.ny + COUNT_TY - 1) / COUNT_TY), (unsigned)((a.nx + a.slab - 1) / a.slab));
         count_rect_kernel<<<grid, COUNT_TY, smem, c->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());

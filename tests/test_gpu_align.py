@@ -422,3 +422,25 @@ def test_host_rectangle_larger_than_one_device_block(engine):
     for k in range(40):
         c = oracle.count(xs[rows[k]].decode(), ys[cols[k]].decode()) or (0, 0, 0, 0)
         assert tuple(free["counts"][rows[k], cols[k]]) == tuple(c)
+
+
+def test_alignment_free_long_sequences(engine):
+    """Pre-aligned rows far longer than a barcode (9 000 and 40 000 columns): the rectangle kernel
+    stages fewer x rows per block instead of refusing."""
+    rng = np.random.default_rng(9000)
+    al = np.frombuffer(b"ACGT-N", dtype=np.uint8)
+    for length, n in ((9000, 20), (40000, 6)):
+        base = al[rng.choice(6, length, p=[0.24, 0.24, 0.24, 0.24, 0.03, 0.01])]
+        seqs = []
+        for _ in range(n):
+            s = base.copy()
+            hit = rng.random(length) < 0.1
+            s[hit] = al[rng.integers(0, 6, int(hit.sum()))]
+            seqs.append(s.tobytes())
+        engine.load(seqs, 0)
+        got = engine.count_rect(0, n, 0, n)
+        for i in range(n):
+            for j in range(n):
+                c = oracle.count(seqs[i].decode(), seqs[j].decode()) or (0, 0, 0, 0)
+                assert tuple(got["counts"][i, j]) == tuple(c), (length, i, j)
+                assert_metrics_close(got["metrics"][i, j][None, :], np.array(oracle.metrics(c))[None, :])
