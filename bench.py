@@ -204,6 +204,19 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # a fresh checkout has no built artefacts (kept out of history): rank 0 builds, the others wait
+    needed = [ROOT / "taxi2_b200" / "lib" / "libtaxi2_b200.so", ROOT / "oracle" / "libtaxi_oracle.so", ROOT / "tools" / "bin" / "int_peak"]
+    if not all(p.exists() for p in needed):
+        if local_rank == 0:
+            import __graft_entry__
+
+            __graft_entry__.build()
+        else:
+            deadline = time.time() + 600
+            while not all(p.exists() for p in needed) and time.time() < deadline:
+                time.sleep(2)
+            time.sleep(5)   # let the linker finish writing
+
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
