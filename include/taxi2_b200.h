@@ -150,6 +150,17 @@ int taxi_format_pairs(const char* path, const int32_t* segments, int32_t nsegmen
 int taxi_format_matrix(const char* path, const char* xid_bytes, const int64_t* xid_off, int32_t x0, int32_t nx, int32_t ny,
                        const double* metrics, const uint8_t* undefined, int32_t column, double scale,
                        const char* float_format, const char* missing, int32_t threads);
+/*
+ * SequencePairHandler.Formatted records (pairs.py:51-97) of the nx*ny pairs of a row block,
+ * appended to `path`: "idx / idy", aligned x, match pattern, aligned y, records separated by an
+ * empty line (first_record != 0: the file is still empty).  aln_* are the arrays
+ * taxi_align_strings filled for these pairs in row-major order.
+ */
+int taxi_format_aligned_pairs(const char* path, int32_t first_record,
+                              const char* xid_bytes, const int64_t* xid_off, const char* yid_bytes, const int64_t* yid_off,
+                              int32_t x0, int32_t nx, int32_t ny,
+                              const uint8_t* aln_x, const uint8_t* aln_y, const int64_t* aln_start, const int64_t* aln_off,
+                              int32_t threads);
 /* SimpleAggregator state (sum, min, max, n, first-seen order) per (subset_x, subset_y), row-major order. */
 int taxi_aggregate_subsets(const double* metrics, const uint8_t* undefined, int32_t x0, int32_t nx, int32_t ny,
                            int32_t column, double scale, const int32_t* xsubset, const int32_t* ysubset, int32_t nsub,

@@ -130,6 +130,52 @@ int taxi_format_matrix(const char* path, const char* xid_bytes, const int64_t* x
     return format_rows(path, nx, threads, fn);
 }
 
+// SequencePairHandler.Formatted records (pairs.py:51-97) for the nx*ny pairs of a row block, pair
+// p = (x0 + p / ny, p % ny): "idx / idy", aligned x, the match pattern ('|' equal and not a gap, '-'
+// either is a gap, '.' otherwise), aligned y; records are separated by one empty line, so every
+// record but the file's first is preceded by "\n".  The gapped strings are the right-aligned
+// slots taxi_align_strings fills: pair p occupies [aln_start[p], aln_off[p + 1]).
+int taxi_format_aligned_pairs(const char* path, int32_t first_record,
+                              const char* xid_bytes, const int64_t* xid_off, const char* yid_bytes, const int64_t* yid_off,
+                              int32_t x0, int32_t nx, int32_t ny,
+                              const uint8_t* aln_x, const uint8_t* aln_y, const int64_t* aln_start, const int64_t* aln_off,
+                              int32_t threads)
+{
+    if (!path || !xid_bytes || !xid_off || !yid_bytes || !yid_off || nx < 0 || ny < 0 || !aln_x || !aln_y || !aln_start || !aln_off)
+        return TAXI_E_ARG;
+    const Table xids{xid_bytes, xid_off}, yids{yid_bytes, yid_off};
+    auto fn = [&](int32_t b, int32_t e, std::string& out) {
+        size_t need = 0;
+        for (int64_t p = (int64_t)b * ny; p < (int64_t)e * ny; ++p) need += 3 * (size_t)(aln_off[p + 1] - aln_start[p]) + 48;
+        out.reserve(need);
+        for (int32_t i = b; i < e; ++i) {
+            for (int32_t j = 0; j < ny; ++j) {
+                const int64_t p = (int64_t)i * ny + j;
+                if (p > 0 || !first_record) out += '\n';
+                xids.append(out, x0 + i);
+                out += " / ";
+                yids.append(out, j);
+                out += '\n';
+                const uint8_t* ax = aln_x + aln_start[p];
+                const uint8_t* ay = aln_y + aln_start[p];
+                const size_t len = (size_t)(aln_off[p + 1] - aln_start[p]);
+                out.append(reinterpret_cast<const char*>(ax), len);
+                out += '\n';
+                const size_t at = out.size();
+                out.resize(at + len);
+                for (size_t k = 0; k < len; ++k) {
+                    const uint8_t a = ax[k], c = ay[k];
+                    out[at + k] = (a == '-' || c == '-') ? '-' : (a == c ? '|' : '.');
+                }
+                out += '\n';
+                out.append(reinterpret_cast<const char*>(ay), len);
+                out += '\n';
+            }
+        }
+    };
+    return format_rows(path, nx, threads, fn);
+}
+
 // SimpleAggregator state per (subset_x, subset_y) for one metric column (versus_all.py:57-95):
 // sum / min / max / n over the defined values in row-major order, plus the order in which the keys
 // first appeared (the reference's dicts iterate in insertion order).  Subset ids are 0..nsub-1, with

@@ -147,8 +147,9 @@ class Engine:
         N.check(self._lib.taxi_align_pairs(self._ctx, _p(px), _p(py), len(px), flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, None)
 
-    def align_strings(self, px, py) -> tuple[list[bytes], list[bytes], np.ndarray]:
-        """-> (aligned x, aligned y, scores) for each pair, Biopython's first alignment."""
+    def align_strings_raw(self, px, py) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """-> (aln_x, aln_y, start, off, scores): pair k's gapped strings are aln_x / aln_y[start[k]:off[k + 1]]
+        (right-aligned in slots of len(x) + len(y) bytes)."""
         px = np.ascontiguousarray(px, dtype=np.int32)
         py = np.ascontiguousarray(py, dtype=np.int32)
         n = len(px)
@@ -160,6 +161,12 @@ class Engine:
         start = np.zeros(max(n, 1), dtype=np.int64)
         score = np.zeros(max(n, 1), dtype=np.int32)
         N.check(self._lib.taxi_align_strings(self._ctx, _p(px), _p(py), n, _p(off), _p(ox), _p(oy), _p(start), _p(score)))
+        return ox, oy, start, off, score[:n]
+
+    def align_strings(self, px, py) -> tuple[list[bytes], list[bytes], np.ndarray]:
+        """-> (aligned x, aligned y, scores) for each pair, Biopython's first alignment."""
+        ox, oy, start, off, score = self.align_strings_raw(px, py)
+        n = len(score)
         bx, by = ox.tobytes(), oy.tobytes()
         ax = [bx[int(start[k]): int(off[k + 1])] for k in range(n)]
         ay = [by[int(start[k]): int(off[k + 1])] for k in range(n)]

@@ -83,6 +83,15 @@ def format_matrix(path, xids: StringTable, x0, nx, ny, metrics, undefined, colum
                                    int(column), float(scale), fmt.encode(), missing.encode(), threads))
 
 
+def format_aligned_pairs(path, first_record: bool, xids: StringTable, yids: StringTable, x0, nx, ny,
+                         aln_x: np.ndarray, aln_y: np.ndarray, aln_start: np.ndarray, aln_off: np.ndarray, threads=0) -> None:
+    """Append the `SequencePairHandler.Formatted` records of a row block (pairs.py:81-97) from the
+    raw arrays of `Engine.align_strings_raw`."""
+    N.check(N.load().taxi_format_aligned_pairs(str(path).encode(), int(bool(first_record)), xids.bytes_ptr, xids.off_ptr,
+                                               yids.bytes_ptr, yids.off_ptr, x0, nx, ny, _ptr(aln_x), _ptr(aln_y),
+                                               _ptr(aln_start), _ptr(aln_off), threads))
+
+
 class NativeSubsetState:
     """sum / min / max / n / first-seen per (subset_x, subset_y) of one metric column."""
 

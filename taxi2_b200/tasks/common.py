@@ -68,12 +68,15 @@ class PairBlock(NamedTuple):
     nx: int
     metrics: np.ndarray          # (nx, ny, 4) float64, NaN = undefined
     aligned: list | None         # nx*ny (aligned_x, aligned_y) strings, or None
+    aligned_raw: tuple | None = None   # (aln_x, aln_y, start, off) arrays of Engine.align_strings_raw, or None
 
 
 def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, align: bool, want_strings: bool,
-                     scores, max_pairs: int = 1 << 20):
+                     scores, max_pairs: int = 1 << 20, raw_strings: bool = False):
     """Drive the device over the row-major product xs x ys (ys=None: xs x xs) in blocks of whole
-    rows, yielding PairBlock in reference order.  One launch per block (plus one for strings)."""
+    rows, yielding PairBlock in reference order.  One launch per block (plus one for strings).
+    raw_strings: hand the gapped strings over as the library's arrays (for the native pair writer)
+    instead of one Python string per sequence."""
     from ..engine import scores_vector
 
     same_set = ys is None
@@ -84,6 +87,8 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
     if not same_set:
         engine.load([s.seq for s in ylist], 1)
     ny = len(ylist)
+    if align and want_strings:
+        max_pairs = min(max_pairs, 1 << 18)   # ~1.3 KB of gapped strings per barcode pair, twice
     rows = max(1, max_pairs // max(ny, 1))
     for x0 in range(0, len(xs), rows):
         nx = min(rows, len(xs) - x0)
@@ -91,9 +96,13 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
             metrics = engine.align_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
         else:
             metrics = engine.count_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
-        aligned = None
+        aligned = aligned_raw = None
         if align and want_strings:
             px, py = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
-            ax, ay, _ = engine.align_strings((px + x0).astype(np.int32), py.astype(np.int32))
-            aligned = [(a.decode("latin-1"), b.decode("latin-1")) for a, b in zip(ax, ay)]
-        yield PairBlock(x0, nx, metrics, aligned)
+            px, py = (px + x0).astype(np.int32), py.astype(np.int32)
+            if raw_strings:
+                aligned_raw = engine.align_strings_raw(px, py)[:4]
+            else:
+                ax, ay, _ = engine.align_strings(px, py)
+                aligned = [(a.decode("latin-1"), b.decode("latin-1")) for a, b in zip(ax, ay)]
+        yield PairBlock(x0, nx, metrics, aligned, aligned_raw)

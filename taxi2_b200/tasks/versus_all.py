@@ -188,10 +188,15 @@ class VersusAll:
         writers = []
         pairs_file = linear_file = None
         matrix_files = []
+        native_pairs = None   # [ids of all sequences, nothing written yet]: the native pair writer appends block by block
         if p.pairs.align and p.pairs.write:
             create_parents(self.paths.aligned_pairs)
-            pairs_file = SequencePairHandler.Formatted(self.paths.aligned_pairs, "w")
-            writers.append(pairs_file)
+            if self.native_writers:
+                Path(self.paths.aligned_pairs).write_bytes(b"")
+                native_pairs = [fastwrite.StringTable([s.id for s in sequences]), True]
+            else:
+                pairs_file = SequencePairHandler.Formatted(self.paths.aligned_pairs, "w")
+                writers.append(pairs_file)
         if p.distances.write_linear:
             create_parents(self.paths.distances_linear)
             linear_file = DistanceHandler.Linear.WithExtras(self.paths.distances_linear, "w", missing=missing, formatter=fmt)
@@ -213,8 +218,13 @@ class VersusAll:
                                    agg_genera, agg_species) if fmtc else None
         same_key = duplicate_groups(sequences)
         try:
-            for block in iter_pair_blocks(engine, sequences, None, p.pairs.align, pairs_file is not None, p.pairs.scores):
+            for block in iter_pair_blocks(engine, sequences, None, p.pairs.align, pairs_file is not None or native_pairs is not None,
+                                          p.pairs.scores, raw_strings=native_pairs is not None):
                 undefined = self._undefined_mask(engine, block, sequences, same_key, p.pairs.align)
+                if native_pairs is not None:
+                    ids, first = native_pairs
+                    fastwrite.format_aligned_pairs(self.paths.aligned_pairs, first, ids, ids, block.x0, block.nx, n, *block.aligned_raw)
+                    native_pairs[1] = False
                 if pairs_file is not None:
                     for bx in range(block.nx):
                         x = sequences[block.x0 + bx]
@@ -284,6 +294,12 @@ class VersusAll:
             for bx, j in cand:
                 ax, ay = block.aligned[bx * n + j]
                 mask[bx, j] = ax == ay
+            return mask
+        if block.aligned_raw is not None:
+            ox, oy, start, off = block.aligned_raw
+            for bx, j in cand:
+                k = bx * n + j
+                mask[bx, j] = np.array_equal(ox[start[k]:off[k + 1]], oy[start[k]:off[k + 1]])
             return mask
         px = np.array([block.x0 + bx for bx, _ in cand], dtype=np.int32)
         py = np.array([j for _, j in cand], dtype=np.int32)

@@ -4,6 +4,8 @@ from __future__ import annotations
 
 from math import inf, isnan
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -118,3 +120,55 @@ def test_comparison_type_column(tmp_path):
                     (False, None): "inter-genus", (False, True): "inter-genus", (False, False): "inter-genus",
                     (True, None): "intra-genus", (True, True): "intra-species", (True, False): "inter-species"}[(sg, ss)]
             assert r == [xs[i].id, ys[j].id, want]
+
+
+def test_aligned_pair_records_match_the_python_handler(tmp_path):
+    """taxi_format_aligned_pairs against SequencePairHandler.Formatted (and the reference's own
+    fixture tests/test_pairs/simple.formatted): same bytes, across two blocks and several threads."""
+    from taxi2_b200.pairs import SequencePair, SequencePairHandler
+
+    rng = np.random.default_rng(8)
+    nx, ny = 5, 4
+    xs = [Sequence(f"x{i}", None) for i in range(nx)]
+    ys = [Sequence(f"id {j}", None) for j in range(ny)]
+    al = np.frombuffer(b"ACGTN-", dtype=np.uint8)
+    pairs, slots = [], []
+    for i in range(nx):
+        for j in range(ny):
+            length = int(rng.integers(1, 40))
+            ax = al[rng.integers(0, 6, length)].tobytes()
+            ay = al[rng.integers(0, 6, length)].tobytes()
+            pairs.append((ax, ay))
+            slots.append(length + int(rng.integers(0, 9)))          # right-aligned in a larger slot
+    off = np.concatenate([[0], np.cumsum(slots)]).astype(np.int64)
+    start = np.array([off[k + 1] - len(pairs[k][0]) for k in range(len(pairs))], dtype=np.int64)
+    ox = np.full(int(off[-1]), ord("?"), dtype=np.uint8)
+    oy = np.full(int(off[-1]), ord("?"), dtype=np.uint8)
+    for k, (ax, ay) in enumerate(pairs):
+        ox[start[k]:off[k + 1]] = np.frombuffer(ax, dtype=np.uint8)
+        oy[start[k]:off[k + 1]] = np.frombuffer(ay, dtype=np.uint8)
+    want = tmp_path / "want.txt"
+    with SequencePairHandler.Formatted(want, "w") as file:
+        for k, (ax, ay) in enumerate(pairs):
+            file.write(SequencePair(Sequence(xs[k // ny].id, ax.decode()), Sequence(ys[k % ny].id, ay.decode())))
+    got = tmp_path / "got.txt"
+    got.write_bytes(b"")
+    xid, yid = fw.StringTable([s.id for s in xs]), fw.StringTable([s.id for s in ys])
+    first = True
+    for x0, rows in ((0, 2), (2, 3)):
+        lo, hi = x0 * ny, (x0 + rows) * ny
+        # a block's arrays start at its own first pair, like a fresh align_strings_raw call
+        boff = off[lo:hi + 1] - off[lo]
+        bstart = start[lo:hi] - off[lo]
+        fw.format_aligned_pairs(got, first, xid, yid, x0, rows, ny, ox[off[lo]:off[hi]].copy(), oy[off[lo]:off[hi]].copy(),
+                                np.ascontiguousarray(bstart), np.ascontiguousarray(boff), threads=3)
+        first = False
+    assert got.read_bytes() == want.read_bytes()
+    # the reference's fixture, through the same entry point
+    fixture = [("id1", "id2", b"ATC-", b"ATG-"), ("id1", "id3", b"ATC-", b"-TAA"), ("id2", "id3", b"ATG-", b"-TAA")]
+    out = tmp_path / "fixture.txt"
+    out.write_bytes(b"")
+    for k, (idx, idy, ax, ay) in enumerate(fixture):
+        fw.format_aligned_pairs(out, k == 0, fw.StringTable([idx]), fw.StringTable([idy]), 0, 1, 1, np.frombuffer(ax, dtype=np.uint8).copy(),
+                                np.frombuffer(ay, dtype=np.uint8).copy(), np.zeros(1, dtype=np.int64), np.array([0, 4], dtype=np.int64))
+    assert out.read_bytes() == (Path(__file__).parent / "golden" / "pairs_simple.formatted").read_bytes()
