@@ -13,6 +13,8 @@ from pathlib import Path
 from time import perf_counter
 from typing import Callable
 
+import numpy as np
+
 from .. import fastwrite
 from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..pairs import SequencePair, SequencePairHandler
@@ -153,16 +155,57 @@ class VersusReference:
                         yield distance, block.metrics[bx, j]
             self.progress_handler("Finalizing...", total, total)
 
+        def write_closest(best: Distance, raw) -> None:
+            closest_file.write(best)
+            for metric, col in zip(extras, extra_cols):
+                d = number_or_none(raw[col])
+                if d is not None:
+                    d *= scale   # adjust_extra_distances: only the non-main metrics are scaled here
+                closest_file.write(Distance(metric, best.x, best.y, d))
+
+        def run_blocks_natively() -> None:
+            """No per-pair Python: linear / matrix rows and aligned pairs through the batch writers,
+            the closest reference of a query as the first minimum of its row (NaN = undefined)."""
+            native_pairs = None
+            if pairs_file is not None:
+                pairs_file.close()
+                Path(self.paths.aligned_pairs).write_bytes(b"")
+                native_pairs = (t_xid, fastwrite.StringTable([s.id for s in reference]))
+            first = True
+            for block in iter_pair_blocks(engine, data, reference, p.pairs.align, native_pairs is not None, p.pairs.scores,
+                                          raw_strings=True):
+                native_block(block)
+                if native_pairs is not None:
+                    fastwrite.format_aligned_pairs(self.paths.aligned_pairs, first, *native_pairs, block.x0, block.nx, nref, *block.aligned_raw)
+                    first = False
+                column = block.metrics[:, :, main_col]
+                undefined = ~np.isfinite(column)
+                for bx in range(block.nx):
+                    if undefined[bx].all():
+                        raise ValueError("min() arg is an empty sequence")   # the reference's min() over no defined distance
+                    j = int(np.argmin(np.where(undefined[bx], np.inf, column[bx])))
+                    x, y = data[block.x0 + bx], reference[j]
+                    if block.aligned_raw is not None:
+                        ox, oy, start, off = block.aligned_raw
+                        k = bx * nref + j
+                        x = Sequence(x.id, ox[start[k]:off[k + 1]].tobytes().decode("latin-1"), x.extras)
+                        y = Sequence(y.id, oy[start[k]:off[k + 1]].tobytes().decode("latin-1"), y.extras)
+                    write_closest(Distance(main, x, y, float(column[bx, j]) * scale), block.metrics[bx, j])
+                state["done"] += block.nx * nref
+                now = perf_counter()
+                if now - state["last"] >= self.progress_interval:
+                    self.progress_handler("distance.x.id", state["done"], total)
+                    state["last"] = now
+            self.progress_handler("Finalizing...", total, total)
+
         try:
+            if fmtc and data and reference:
+                run_blocks_natively()
+                return Results(self.work_dir, perf_counter() - ts)
             for _, group in groupby(main_distances(), lambda item: item[0].x.id):
                 defined = [item for item in group if item[0].d is not None]
                 best, raw = min(defined, key=lambda item: item[0].d)   # ValueError on an empty group, like the reference
-                closest_file.write(best)
-                for metric, col in zip(extras, extra_cols):
-                    d = number_or_none(raw[col])
-                    if d is not None:
-                        d *= scale   # adjust_extra_distances: only the non-main metrics are scaled here
-                    closest_file.write(Distance(metric, best.x, best.y, d))
+                write_closest(best, raw)
         finally:
             for w in writers:
                 w.close()
