@@ -15,6 +15,9 @@ from pathlib import Path
 from time import perf_counter
 from typing import Callable
 
+import numpy as np
+
+from .. import fastwrite
 from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..files import FileFormat, identify_format
 from ..handlers import FileHandler
@@ -32,6 +35,7 @@ class _DecontaminateBase:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.native_writers: bool = True   # batch writers and row minima without per-pair Python (same bytes)
         self.input: Sequences = None
         self.outgroup: Sequences = None
         self.output_format: FileFormat = None
@@ -95,7 +99,46 @@ class _DecontaminateBase:
                             matrix_file.write(distance)
                         yield distance
 
+        def minimums_by_block():
+            """The same stream without per-pair Python: rows of the linear / matrix files and the aligned
+            pairs through the batch writers, the minimum of a query as the first minimum of its row
+            (undefined counts as +inf; a row with nothing defined yields its first pair, like min())."""
+            fill = lambda values: [missing if v is None else v for v in values]  # noqa: E731
+            t_x = fastwrite.StringTable(["\t".join([s.id, *fill(s.extras.values())]) for s in xs])
+            t_y = fastwrite.StringTable(["\t".join([s.id, *fill(s.extras.values())]) for s in ys])
+            t_xid = fastwrite.StringTable([s.id for s in xs])
+            t_yid = fastwrite.StringTable([s.id for s in ys])
+            for handle, path, header in (
+                    (linear_file, linear_path, ("seqid (query)", *(k + " (query)" for k in xs[0].extras), "seqid (reference)",
+                                                *(k + " (reference)" for k in ys[0].extras), str(metric))),
+                    (matrix_file, matrix_path, ("", *(s.id for s in ys))),
+                    (pairs_file, pairs_path, None)):
+                if handle is not None:
+                    handle.close()
+                    Path(path).write_text("" if header is None else "\t".join(header) + "\n")
+            first = True
+            for block in iter_pair_blocks(engine, xs, ys, p.pairs.align, pairs_file is not None, p.pairs.scores, raw_strings=True):
+                if linear_file is not None:
+                    fastwrite.format_pairs(linear_path, [fastwrite.SEG_X[0], fastwrite.SEG_Y[0], fastwrite.SEG_SCORES], [t_x], [t_y],
+                                           block.x0, block.nx, len(ys), block.metrics, None, [col], scale, fmtc, missing)
+                if matrix_file is not None:
+                    fastwrite.format_matrix(matrix_path, t_xid, block.x0, block.nx, len(ys), block.metrics, None, col, scale, fmtc, missing)
+                if pairs_file is not None:
+                    fastwrite.format_aligned_pairs(pairs_path, first, t_xid, t_yid, block.x0, block.nx, len(ys), *block.aligned_raw)
+                    first = False
+                column = block.metrics[:, :, col]
+                undefined = ~np.isfinite(column)
+                for bx in range(block.nx):
+                    j = int(np.argmin(np.where(undefined[bx], np.inf, column[bx])))
+                    d = None if undefined[bx, j] else float(column[bx, j]) * scale
+                    yield Distance(metric, xs[block.x0 + bx], ys[j], d)
+
+        fmtc = fastwrite.printf_format(fmt) if self.native_writers else None
+        distinct = all(a.id != b.id for a, b in zip(xs, xs[1:]))   # groupby(x.id) would merge equal neighbours
         try:
+            if fmtc and xs and ys and distinct:
+                yield from minimums_by_block()
+                return
             for _, grp in groupby(distances(), lambda d: d.x.id):
                 yield min(grp, key=lambda d: d.d if d.d is not None else inf)
         finally:

@@ -199,7 +199,10 @@ class VersusReference:
             self.progress_handler("Finalizing...", total, total)
 
         try:
-            if fmtc and data and reference:
+            # groupby(x.id) merges consecutive queries that share an id into one group (reference quirk):
+            # such inputs take the per-pair path, which reproduces it
+            distinct = all(a.id != b.id for a, b in zip(data, data[1:]))
+            if fmtc and data and reference and distinct:
                 run_blocks_natively()
                 return Results(self.work_dir, perf_counter() - ts)
             for _, group in groupby(main_distances(), lambda item: item[0].x.id):

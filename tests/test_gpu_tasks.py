@@ -173,14 +173,16 @@ def test_dereplicate_outputs(tmp_path, align, write, multiply, fasta):
     assert_same_tree(task.work_dir, tmp_path / "want")
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("align,multiply,fasta", [(True, False, False), (True, True, True), (False, False, False)])
-def test_decontaminate_outputs(tmp_path, align, multiply, fasta):
+def test_decontaminate_outputs(tmp_path, align, multiply, fasta, native):
     seqs, _, _ = load("Taxi2test1_50.tab")
     records = list(seqs)
     data, outgroup, ingroup = records[:14], records[14:30], records[30:46]
     data.append(Sequence("allN", "nnnnnnnn", records[0].extras))
     task = Decontaminate()
     task.work_dir = tmp_path / "got1"
+    task.native_writers = native   # block path vs per-pair path: same bytes
     task.progress_handler = SILENT
     task.input, task.outgroup = Sequences(data), Sequences(outgroup)
     task.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
@@ -194,6 +196,7 @@ def test_decontaminate_outputs(tmp_path, align, multiply, fasta):
 
     task2 = Decontaminate2()
     task2.work_dir = tmp_path / "got2"
+    task2.native_writers = native
     task2.progress_handler = SILENT
     task2.input, task2.outgroup, task2.ingroup = Sequences(data), Sequences(outgroup), Sequences(ingroup)
     task2.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
