@@ -37,12 +37,22 @@ struct Fast16 {
     int32_t has_gap_symbol;            // '-' occurs inside the loaded sequences (input that was not normalized)
 };
 
+// Symbol codes are stored per sequence with CODE_LEAD pad codes (7 = "matches nothing") in front
+// and one behind, so the DP's one-step-ahead fetch of the next column symbol needs no lower bound
+// check at all (the wavefront skew is at most 31 columns) and only a clamp at the upper end.
+constexpr int CODE_LEAD = 32;
+constexpr int CODE_PAD = CODE_LEAD + 1;
+__host__ __device__ __forceinline__ long long code_offset(long long byte_offset, long long index)
+{
+    return byte_offset + index * CODE_PAD + CODE_LEAD;
+}
+
 struct PairIndex { int xi, yi; long long out; };
 
 struct AlignArgs {
     const uint8_t* xb; const int64_t* xoff;   // row set (x): bytes + offsets
     const uint8_t* yb; const int64_t* yoff;   // column set (y)
-    const uint8_t* xc; const uint8_t* yc;     // 3-bit symbol codes (same offsets), fast path only
+    const uint8_t* xc; const uint8_t* yc;     // 3-bit symbol codes at code_offset(offset, index), fast path only
     Fast16 f16;
     const int32_t* px; const int32_t* py;     // explicit pair list, or nullptr for rect mode
     int32_t x0, y0, ny;                       // rect mode: pair p = (x0 + p / ny, y0 + p % ny)

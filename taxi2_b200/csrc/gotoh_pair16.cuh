@@ -248,7 +248,7 @@ __device__ __forceinline__ PairRef pair_ref(const AlignArgs& a, long long p)
     const int64_t xo = a.xoff[xi], yo = a.yoff[yi];
     PairRef r;
     r.out = pi.out;
-    r.xc = a.xc + xo; r.yc = a.yc + yo;
+    r.xc = a.xc + code_offset(xo, xi); r.yc = a.yc + code_offset(yo, yi);
     r.nA = (int)(a.xoff[xi + 1] - xo);
     r.nB = (int)(a.yoff[yi + 1] - yo);
     return r;
@@ -428,9 +428,11 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     uint8_t* tbase = trace + (size_t)lane * HB;
     const int tA = A.nB - 1 + (31 - l0), tB = B.nB - 1 + (31 - l0);   // steps at which lane 31 finishes column nB
     // symbols of y are fetched one step ahead so that the load latency hides behind a whole step
+    // (jj >= -30 always: the pad codes in front of every sequence cover it; past the end the clamp
+    // lands on the pad code behind it)
     auto fetch_b = [&](int jj, uint32_t& o0, uint32_t& o1) {
-        o0 = (jj >= 1 && jj <= A.nB) ? (uint32_t)__ldg(A.yc + jj - 1) : PAD;
-        o1 = (jj >= 1 && jj <= B.nB) ? (uint32_t)__ldg(B.yc + jj - 1) : PAD;
+        o0 = (uint32_t)__ldg(A.yc + min(jj, A.nB + 1) - 1);
+        o1 = (uint32_t)__ldg(B.yc + min(jj, B.nB + 1) - 1);
     };
     uint32_t nb0, nb1;
     fetch_b(0 - (lane - l0) + 1, nb0, nb1);

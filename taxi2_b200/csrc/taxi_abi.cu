@@ -161,15 +161,21 @@ const Dispatch kDispatch[] = {
     {32, occupancy<32>, launch_gotoh<32>, TraceGeom<32>::HB},
 };
 
-// bytes -> 3-bit symbol codes through the context codebook (coalesced, one thread per 4 bytes)
-__global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, int64_t n, const uint8_t* __restrict__ book,
-                                    uint8_t* __restrict__ out)
+// bytes -> 3-bit symbol codes through the context codebook, in the padded per-sequence layout of
+// code_offset(): one block per sequence (grid-stride), CODE_LEAD pad codes, the codes, one pad code
+__global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ off, int32_t nseq,
+                                    const uint8_t* __restrict__ book, uint8_t* __restrict__ out)
 {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x & 255] = book[threadIdx.x & 255];
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = lut[bytes[k]];
+    for (int32_t seq = blockIdx.x; seq < nseq; seq += gridDim.x) {
+        const int64_t o = off[seq];
+        const int len = (int)(off[seq + 1] - o);
+        uint8_t* dst = out + code_offset(o, seq) - CODE_LEAD;
+        for (int k = threadIdx.x; k < len + CODE_PAD; k += blockDim.x)
+            dst[k] = (k < CODE_LEAD || k == CODE_LEAD + len) ? (uint8_t)7 : lut[bytes[o + k - CODE_LEAD]];
+    }
 }
 
 template <int H, int MODE> cudaError_t occupancy16(int* blocks_per_sm)
@@ -555,9 +561,9 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
         CUDA_TRY(c->d_codebook.reserve(256));
         CUDA_TRY(cudaMemcpyAsync(c->d_codebook.p, book, 256, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // `book` is a stack buffer
-        CUDA_TRY(s.codes.reserve((size_t)s.total + 16, 1));
-        if (s.total) {
-            encode_codes_kernel<<<(unsigned)std::min<int64_t>((s.total + 255) / 256, 4096), 256, 0, c->stream>>>(s.bytes.p, s.total, c->d_codebook.p, s.codes.p);
+        CUDA_TRY(s.codes.reserve((size_t)s.total + (size_t)CODE_PAD * (size_t)std::max(n, 1) + 16, 1));
+        if (n > 0) {
+            encode_codes_kernel<<<(unsigned)std::min<int32_t>(n, 8192), 256, 0, c->stream>>>(s.bytes.p, s.d_off.p, n, c->d_codebook.p, s.codes.p);
             CUDA_TRY(cudaGetLastError());
         }
         // a symbol first seen in set 1 extends the book: set 0 was encoded with the older book,
