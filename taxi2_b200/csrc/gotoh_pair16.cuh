@@ -650,7 +650,7 @@ constexpr int PAIR16_WARPS_PER_BLOCK = PAIR16_WPB;
 // Three blocks of four warps (168 registers) is the measured optimum for the 21-row kernel; the
 // taller / multi-stripe instantiations need more registers and run two blocks per SM.
 template <int H, int MODE>
-__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, (H >= 24 || MODE == 2) ? 2 : PAIR16_MIN_BLOCKS)
+__global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, (H >= 32) ? 2 : PAIR16_MIN_BLOCKS)
 gotoh_pair16_kernel(const AlignArgs a)
 {
     const int lane = threadIdx.x & 31;

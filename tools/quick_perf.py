@@ -1,5 +1,5 @@
 """Quick device-side throughput probe (not the bench contract): GCUPS of one rect launch.
-usage: quick_perf.py [n] [option=value ...]   e.g.  quick_perf.py 1024 force_top=1"""
+usage: quick_perf.py [n] [option=value ...]   e.g.  quick_perf.py 1024 force_top=1 length=1200"""
 import json
 import sys
 import time
@@ -12,10 +12,10 @@ from synth import coi_like  # noqa: E402
 from taxi2_b200.engine import Engine  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-seqs = coi_like(n, seed=650)
+options = dict(opt.split("=") for opt in sys.argv[2:])
+seqs = coi_like(n, length=int(options.pop("length", 650)), seed=650)
 eng = Engine(0)
-for opt in sys.argv[2:]:
-    k, v = opt.split("=")
+for k, v in options.items():
     eng.set_option(k, int(v))
 eng.load(seqs, 0)
 counts = torch.empty((n * n, 4), dtype=torch.int32, device="cuda")
