@@ -562,6 +562,16 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
         uint8_t* tbase = trace + ((size_t)st * stride * 32 + lane) * HB;
         const int tA = last ? A.nB - 1 + (31 - first_lane) : -2, tB = last ? B.nB - 1 + (31 - first_lane) : -2;
         int t = 0;
+        // the y symbols of a column and, for the top slot of a later stripe, the values the previous
+        // stripe left in the boundary buffer are fetched one step ahead, so that their latency hides
+        // behind a whole step (the pad codes around every sequence make the symbol fetch a clamp)
+        uint32_t nb0 = PAD, nb1 = PAD, nbX = NEG2, nbH = NEG2;
+        auto fetch_next = [&](int jj) {
+            nb0 = (uint32_t)__ldg(A.yc + min(jj, A.nB + 1) - 1);
+            nb1 = (uint32_t)__ldg(B.yc + min(jj, B.nB + 1) - 1);
+            if (lane == 0 && st > 0) { nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1); }   // lane 0: jj >= 1
+        };
+        fetch_next(0 - (lane - first_lane) + 1);
 #pragma unroll 1
         for (int seg = 0; seg < 3; ++seg) {
             const int tend = !last ? (seg == 2 ? nsteps : 0) : ((seg == 0) ? min(tA, tB) + 1 : (seg == 1 ? max(tA, tB) + 1 : nsteps));
@@ -570,13 +580,13 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
                 uint32_t rX = __shfl_up_sync(TAXI_FULL_MASK, outX, 1);
                 uint32_t rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
                 const bool active = live && j >= 1 && j <= nBmax;
+                const uint32_t b0 = nb0, b1 = nb1;
                 if (lane == 0) {
                     if (st == 0 || !active) { rX = NEG2; rH = NEG2; }
-                    else { rX = __ldcg(bnd + 2 * j); rH = __ldcg(bnd + 2 * j + 1); }
+                    else { rX = nbX; rH = nbH; }
                 }
+                fetch_next(j + 1);
                 if (active) {
-                    const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : PAD;
-                    const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : PAD;
                     const uint32_t b2 = b0 | (b1 << 8);
                     auto sub_of = [&](int r) -> uint32_t { return prmt_raw(f.tlo, f.thi, lop3_xor_or(a2[r], b2, 0x8080u)); };
                     uint32_t ncXM = ncXMi, cXX = cXXi;
