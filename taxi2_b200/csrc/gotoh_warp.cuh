@@ -104,11 +104,23 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
         int outX = 0, outH = 0;
         uint8_t* tbase = trace + ((size_t)s * step_stride * 32 + lane) * HB;
 
+        // the y symbol of a column and, for the top rows of a later stripe, the values the previous
+        // stripe left in the boundary buffer are fetched one step ahead: their latency hides behind a
+        // whole step instead of stalling the warp at the top of it
+        int nb = 0, nbX = 0, nbH = 0;
+        auto fetch_next = [&](int jj) {
+            if (live && jj >= 1 && jj <= nB) {
+                nb = (int)__ldg(y + jj - 1);
+                if (lane == 0 && s > 0) { nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1); }
+            }
+        };
+        fetch_next(1 - lane);
         for (int t = 0; t < nsteps; ++t) {
             const int j = t - lane + 1;
             int rX = __shfl_up_sync(TAXI_FULL_MASK, outX, 1);
             int rH = __shfl_up_sync(TAXI_FULL_MASK, outH, 1);
             const bool active = live && j >= 1 && j <= nB;
+            const int b = nb;
             if (lane == 0 && active) {
                 if (s == 0) {
                     // row 0 of the matrix: only Iy is alive there (leading end gap of j columns)
@@ -116,12 +128,12 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                     rH = y0j | sc.tagY;
                     rX = (y0j + (j == nB ? sc.eo : sc.io)) | sc.tagY;
                 } else {
-                    rX = __ldcg(bnd + 2 * j);
-                    rH = __ldcg(bnd + 2 * j + 1);
+                    rX = nbX;
+                    rH = nbH;
                 }
             }
+            fetch_next(j + 1);
             if (active) {
-                const int b = (int)__ldg(y + j - 1);
                 const int cXo = (j == nB) ? sc.eo : sc.io;  // vertical gaps in the last column are end gaps
                 const int cXe = (j == nB) ? sc.ee : sc.ie;
                 int Hd = Hd_saved;
