@@ -32,7 +32,8 @@ typedef enum {
     TAXI_E_RANGE = -5     /* scores or lengths outside what the integer DP represents exactly */
 } taxi_status;
 
-typedef struct taxi_ctx taxi_ctx; /* one per (process, device); not thread-safe */
+typedef struct taxi_ctx taxi_ctx; /* one per (process, device); a context is not thread-safe, but contexts of
+                                     different devices may be driven by different host threads concurrently */
 
 /* Scores.defaults order (align.py:20-27): match, mismatch, internal open, internal extend,
    end open, end extend.  Integer scores only (Scores is dict[str,int], align.py:17). */
@@ -102,6 +103,14 @@ int taxi_alignment_capacity(taxi_ctx* ctx, const int32_t* px, const int32_t* py,
 int taxi_align_strings(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs,
                        const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
                        int32_t* out_score);
+/*
+ * Same launch, with the distance counts / metrics of taxi_align_pairs as well: what a task needs
+ * when it writes aligned pairs AND distances (versus_all.py:527-552 aligns once and feeds both
+ * writers from that one alignment).  Any of out_score / out_counts / out_metrics may be NULL.
+ */
+int taxi_align_strings_metrics(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_t npairs,
+                               const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
+                               uint32_t flags, int32_t* out_score, int32_t* out_counts, double* out_metrics);
 
 /*
  * Alignment-free mode (params.pairs.align = False, versus_all.py:522-530): per-pair counts and
@@ -122,6 +131,18 @@ int taxi_count_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_
  */
 int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
                             int32_t* out_index_host, double* out_value_host);
+
+/*
+ * versusReference at scale (BASELINE config C4): for every query row x0..x0+nx the best match over
+ * the reference columns [y0, y0+ny) -- alignment (align != 0) or alignment-free counting of the
+ * rectangle in device-resident blocks, first minimum of metric column `metric` per row, and the
+ * whole winning pair: out_index[x] = its column (index into set 1; -1 = the row has no defined
+ * distance), out_metrics[x][4], out_counts[x][4] (either may be NULL).  Only the winners leave the
+ * device.  Column ranges of the same rows computed by different calls (or devices) are combined
+ * on the host: smaller value wins, ties go to the smaller column index.
+ */
+int taxi_best_rows(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, int32_t metric, int32_t align,
+                   int32_t* out_index, double* out_metrics, int32_t* out_counts);
 
 /*
  * Host-side batch formatter and subset aggregator (no GPU involved; taxi2_b200/csrc/host_format.cpp)

@@ -35,6 +35,7 @@ struct Fast16 {
     uint32_t class_lut;                // nibble k = base_class of the symbol with code k (traceback counts work on codes)
     uint32_t ascii_lo, ascii_hi;       // byte k = the symbol with code k (gapped strings are written from codes)
     int32_t has_gap_symbol;            // '-' occurs inside the loaded sequences (input that was not normalized)
+    int32_t dead_extra;                // largest difference of the x lengths of the two pairs of a unit that `neg` is budgeted for
 };
 
 // Symbol codes are stored per sequence with CODE_LEAD pad codes (7 = "matches nothing") in front
@@ -62,6 +63,13 @@ struct AlignArgs {
                                               // of the rectangle's columns, longest first, so that the two pairs of a warp and
                                               // consecutive work units have similar lengths)
     long long npairs;
+    // packed kernel (two pairs per warp unit).  The two pairs of a unit must have (nearly) the same
+    // x length: the bottom-aligned variants keep the shorter pair's extra slots dead, and the dead
+    // band is budgeted for at most Fast16::dead_extra of them.  Rect mode: a unit is two consecutive
+    // columns of ONE row (the last unit of an odd-width row holds a single pair), so the x lengths
+    // are equal by construction.  Pair-list mode: the host pairs the list by length (unit_pairs).
+    long long nunits;
+    const int32_t* unit_pairs;                // pair-list mode: unit u aligns pairs unit_pairs[2u], unit_pairs[2u+1] (equal = one pair)
     ScoreSet sc;
     int32_t* score;                           // [npairs] or nullptr
     int32_t* counts;                          // [npairs][4] or nullptr

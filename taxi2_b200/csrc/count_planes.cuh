@@ -187,4 +187,35 @@ __global__ void argmin_rows_kernel(const double* __restrict__ metrics, int32_t n
     }
 }
 
+// Same reduction, returning the whole winning pair: index (offset by col0, -1 = no defined
+// distance in the row), its four metrics and its four counts -- what VersusReference needs per
+// query (versus_reference.py:119-129,184-188), so the nx x ny matrix never leaves the device.
+__global__ void best_rows_kernel(const double* __restrict__ metrics, const int32_t* __restrict__ counts, int32_t nx, int32_t ny,
+                                 int32_t metric, int32_t col0, int32_t* __restrict__ out_idx, double* __restrict__ out_metrics,
+                                 int32_t* __restrict__ out_counts)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nx) return;
+    double best = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+    int bidx = 0x7fffffff;
+    for (int c = lane; c < ny; c += 32) {
+        const double v = metrics[((size_t)row * ny + c) * 4 + metric];
+        if (v == v && (v < best || (v == best && c < bidx))) { best = v; bidx = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(TAXI_FULL_MASK, best, o);
+        const int oi = __shfl_xor_sync(TAXI_FULL_MASK, bidx, o);
+        if (oi != 0x7fffffff && (bidx == 0x7fffffff || ov < best || (ov == best && oi < bidx))) { best = ov; bidx = oi; }
+    }
+    const bool none = bidx == 0x7fffffff;
+    if (lane == 0) out_idx[row] = none ? -1 : col0 + bidx;
+    if (lane < 4) {
+        const size_t at = ((size_t)row * ny + (none ? 0 : bidx)) * 4 + lane;
+        out_metrics[(size_t)row * 4 + lane] = none ? __longlong_as_double(0x7ff8000000000000LL) : metrics[at];
+        if (counts && out_counts) out_counts[(size_t)row * 4 + lane] = none ? 0 : counts[at];
+    }
+}
+
 }  // namespace taxi

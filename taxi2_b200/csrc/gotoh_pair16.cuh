@@ -667,14 +667,21 @@ gotoh_pair16_kernel(const AlignArgs a)
     const long long gw = (long long)blockIdx.x * PAIR16_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     uint8_t* trace = a.trace + gw * a.trace_per_warp;
     uint32_t* bnd = reinterpret_cast<uint32_t*>(a.bnd + gw * a.bnd_per_warp);
-    const unsigned long long units = ((unsigned long long)a.npairs + 1ULL) / 2ULL;
+    const unsigned long long units = (unsigned long long)a.nunits;
+    const unsigned long long upr = ((unsigned long long)a.ny + 1ULL) / 2ULL;   // rect mode: units per row
     for (;;) {
         unsigned long long u = 0;
         if (lane == 0) u = atomicAdd(a.counter, 1ULL);
         u = __shfl_sync(TAXI_FULL_MASK, u, 0);
         if (u >= units) break;
-        const long long p0 = (long long)(2ULL * u);
-        const long long p1 = (p0 + 1 < a.npairs) ? p0 + 1 : p0;
+        long long p0, p1;
+        if (a.unit_pairs) {
+            p0 = a.unit_pairs[2 * u]; p1 = a.unit_pairs[2 * u + 1];
+        } else {
+            const unsigned long long row = u / upr, cu = u % upr;
+            p0 = (long long)(row * (unsigned long long)a.ny + 2ULL * cu);
+            p1 = (2ULL * cu + 1ULL < (unsigned long long)a.ny) ? p0 + 1 : p0;
+        }
         if constexpr (MODE == 2) align_two_bottom_multi<H>(a, p0, p1, lane, trace, bnd);
         else if constexpr (MODE == 1) align_two_bottom<H>(a, p0, p1, lane, trace);
         else align_two<H>(a, p0, p1, lane, trace);

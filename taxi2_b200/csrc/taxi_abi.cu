@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -97,13 +98,14 @@ struct taxi_ctx {
     DevBuf<int32_t> bnd;
     DevBuf<unsigned long long> counter;
     DevBuf<int> status;
-    DevBuf<int32_t> d_px, d_py, d_xrows, d_ycols;
+    DevBuf<int32_t> d_px, d_py, d_xrows, d_ycols, d_units;
+    std::vector<int32_t> h_la, h_lb, h_units;   // pair-list calls: x / y length of every pair, warp units of the packed kernel
     DevBuf<int32_t> d_score, d_counts;
     DevBuf<double> d_metrics;
     DevBuf<uint8_t> d_alnx, d_alny;
     DevBuf<int64_t> d_alnoff, d_alnstart;
-    DevBuf<int32_t> d_argidx;
-    DevBuf<double> d_argval;
+    DevBuf<int32_t> d_argidx, d_bestcounts;
+    DevBuf<double> d_argval, d_bestmetrics;
     // stats of the last call
     int64_t launches = 0, cells = 0;
     double kernel_ms = 0.0;
@@ -197,7 +199,10 @@ const Dispatch kDispatch16m[] = {P16(16, 2), P16(21, 2), P16(24, 2), P16(32, 2)}
 #undef P16
 
 // Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
-bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out, int* H_out, int* mode_out)
+// dead_extra: largest difference between the x lengths of the two pairs of a warp unit (0 for
+// rectangles).  *max_dead_out (optional) receives the largest dead_extra that would still fit.
+bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, int dead_extra, Fast16* out, int* H_out, int* mode_out,
+                     long long* max_dead_out = nullptr)
 {
     if (c->force_general || !c->codebook_ok) return false;
     const int32_t* s = c->raw_scores;
@@ -252,10 +257,17 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     // Range.  The best transformed value is 0 (all matches), so the bias sits at the top of the
     // window.  Lowest real value of the padded DP: a leading end gap to the diagonal followed by
     // mismatches -- linear in (i, j), so its extreme is at a corner -- plus one gap opening for the
-    // Ix / Iy states.  Dead slots idle between `neg` and neg - (H*D16 + one penalty): each dead row
-    // is at most one mismatch below the row above it, and the top one is fed the constant `neg`.
+    // Ix / Iy states.
+    // Dead slots (bottom-aligned variants: the slots above row 0 of a pair, inside the lanes that
+    // are live for the unit) idle below `neg`: the topmost one is fed the constant `neg` from
+    // above, and every further one sits at most one vertical extension below its upper neighbour
+    // (H >= Ix >= Ix(above) - extend; the M and Iy candidates are then within one mismatch / one
+    // opening of that).  A pair has at most H - 1 dead slots of its own plus, when its partner in
+    // the unit has a longer x, the difference of the two x lengths (dead_extra).  `neg` must keep
+    // the whole dead band non-negative -- a value that wraps below 0 reappears at the top of the
+    // unsigned window and beats every real score -- and below every reachable real value.
     // (bottom-aligned variants pad ABOVE row 0 with dead slots, so their DP has max_rows real rows;
-    //  the top-aligned variant pads below row nA with rows that extend the DP)
+    //  the top-aligned variant pads below row nA with rows that extend the DP and has no dead slots)
     if (mode != 0) R = max_rows;
     const long long C = max_cols;
     const long long pen_e = std::max({f.PeX, f.PeeX, f.PeY, f.PeeY});
@@ -266,9 +278,14 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
     const long long corner_h = f.PeoY + C * f.PeeY;                                   // (0, C)
     const long long corner_d = m * f.D16 + (R > C ? f.PeoX + (R - C) * f.PeeX : f.PeoY + (C - R) * f.PeeY);   // (R, C)
     const long long lower = std::max({corner_v, corner_h, corner_d}) + pen_o + pen_e;
-    const long long neg = ((long long)H * f.D16 + pen_o + pen_e + 512 + 15) / 16 * 16;
+    const long long dead_step = std::max<long long>({f.D16, f.PeX, f.PeeX, 16});
+    const long long dead_fixed = pen_o + pen_e + f.D16 + 512 + 15;
     const long long bias = (65535 - 256) / 16 * 16;
-    if (bias - lower < neg + 256) return false;
+    const long long room = bias - lower - 256;                                        // largest admissible neg
+    if (max_dead_out) *max_dead_out = (mode == 0) ? (1LL << 40) : (room - dead_fixed) / dead_step - H;
+    const long long neg = ((mode == 0 ? (long long)H : (long long)H + dead_extra) * dead_step + dead_fixed) / 16 * 16;
+    if (neg > room) return false;
+    f.dead_extra = dead_extra;
     f.bias = (int32_t)bias; f.neg = (int32_t)neg;
     *out = f; *H_out = H;
     *mode_out = mode;
@@ -277,12 +294,65 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, Fast16* out,
 
 // Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
 // pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.
+// Pair-list launches of the packed kernel: which two pairs share a warp.  Pairs are visited by
+// decreasing x length (then y length), so the two pairs of a unit sweep about the same rows and
+// columns and the longest units are handed out first; two neighbours share a unit only if their
+// x lengths differ by at most `max_dead` (see fast16_eligible), else a pair runs alone.
+// Returns the largest difference actually used.
+int build_units(taxi_ctx* c, long long npairs, long long max_dead)
+{
+    std::vector<int32_t> order((size_t)npairs);
+    for (long long k = 0; k < npairs; ++k) order[(size_t)k] = (int32_t)k;
+    const std::vector<int32_t>& la = c->h_la;
+    const std::vector<int32_t>& lb = c->h_lb;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t u, int32_t v) {
+        return la[u] != la[v] ? la[u] > la[v] : lb[u] > lb[v];
+    });
+    c->h_units.clear();
+    c->h_units.reserve((size_t)npairs + 1);
+    int used = 0;
+    for (long long k = 0; k < npairs;) {
+        const int32_t p0 = order[(size_t)k];
+        if (k + 1 < npairs && (long long)la[p0] - la[order[(size_t)k + 1]] <= max_dead) {
+            const int32_t p1 = order[(size_t)k + 1];
+            used = std::max(used, la[p0] - la[p1]);
+            c->h_units.push_back(p0); c->h_units.push_back(p1);
+            k += 2;
+        } else {
+            c->h_units.push_back(p0); c->h_units.push_back(p0);
+            k += 1;
+        }
+    }
+    return used;
+}
+
+// Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
+// pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.  Pair-list
+// launches (a.px set) expect the lengths of every pair in c->h_la / c->h_lb (upload_pairs).
 int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool record_start = true, bool reset_work = true)
 {
     Fast16 f16{};
     int H = 0;
     int mode = 0;
-    const bool fast = fast16_eligible(c, max_rows, max_cols, &f16, &H, &mode);
+    long long max_dead = 0;
+    bool fast = fast16_eligible(c, max_rows, max_cols, 0, &f16, &H, &mode, &max_dead);
+    a.unit_pairs = nullptr;
+    a.nunits = 0;
+    if (fast && a.px) {
+        if (a.npairs >= (1LL << 31)) return fail(TAXI_E_ARG, "pair list too long (%lld)", a.npairs);
+        const int used = build_units(c, a.npairs, std::max<long long>(0, max_dead));
+        if (used > 0 && mode != 0) {
+            fast = fast16_eligible(c, max_rows, max_cols, used, &f16, &H, &mode);
+            if (!fast) return fail(TAXI_E_RANGE, "internal: dead-band budget (%d) rejected", used);
+        }
+        CUDA_TRY(c->d_units.reserve(c->h_units.size(), 1));
+        CUDA_TRY(cudaMemcpyAsync(c->d_units.p, c->h_units.data(), c->h_units.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // h_units may be rebuilt by the next call
+        a.unit_pairs = c->d_units.p;
+        a.nunits = (long long)(c->h_units.size() / 2);
+    } else if (fast) {
+        a.nunits = (a.npairs / a.ny) * (((long long)a.ny + 1) / 2);   // whole rows: npairs = rows * ny
+    }
     if (!fast) H = pick_H(max_rows);
     const Dispatch* d = nullptr;
     if (fast) {
@@ -290,14 +360,19 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
         else { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
     }
     else { for (const auto& e : kDispatch) if (e.H == H) d = &e; }
-    // occupancy of each kernel variant is queried once per process
+    // occupancy of each kernel variant is queried once per process (contexts of several devices
+    // may run on several host threads: the cache is shared and locked)
     static std::map<const Dispatch*, int> occupancy_cache;
+    static std::mutex occupancy_lock;
     int bps = 0;
-    auto hit = occupancy_cache.find(d);
-    if (hit != occupancy_cache.end()) bps = hit->second;
-    else {
-        CUDA_TRY(d->occ(&bps));
-        occupancy_cache[d] = bps;
+    {
+        std::lock_guard<std::mutex> guard(occupancy_lock);
+        auto hit = occupancy_cache.find(d);
+        if (hit != occupancy_cache.end()) bps = hit->second;
+        else {
+            CUDA_TRY(d->occ(&bps));
+            occupancy_cache[d] = bps;
+        }
     }
     if (bps < 1) return fail(TAXI_E_CUDA, "gotoh kernel does not fit on an SM");
     const long long SL = 32LL * H;
@@ -308,7 +383,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     const long long arena_cols = (std::max<long long>(max_cols, yset(c).maxlen) + 255) / 128 * 128;   // + headroom for reloaded sets
     const long long per_warp = ((nstripes * (arena_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (arena_cols + 2);
-    const long long work_units = fast ? (a.npairs + 1) / 2 : a.npairs;
+    const long long work_units = fast ? a.nunits : a.npairs;
     c->last_kernel = fast ? 16 + mode : 32;
     a.f16 = f16;
     // resident warps, capped by pairs and by a trace-arena budget of half the free memory
@@ -328,7 +403,6 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     CUDA_TRY(c->counter.reserve(1));
     CUDA_TRY(c->status.reserve(1));
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
-    if (reset_work) CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
     a.sc = c->sc;
     a.trace = c->trace.p; a.trace_per_warp = per_warp;
     a.bnd = c->bnd.p; a.bnd_per_warp = bnd_per_warp;
@@ -343,11 +417,15 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
 
 int finish_align(taxi_ctx* c)
 {
+    CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms += ms;
+    // the device-side error flag is sticky: kernels only ever set it, and it is cleared here, after
+    // it has been read, so that a *_device launch enqueued before another cannot lose its error
     int st = 0;
-    if (c->status.p) CUDA_TRY(cudaMemcpy(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&st, c->status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) CUDA_TRY(cudaMemset(c->status.p, 0, sizeof(int)));
     if (st == TAXI_E_EMPTY) return fail(TAXI_E_EMPTY, "sequence has zero length");
     if (st != 0) return fail(st, "device status %d", st);
     return TAXI_OK;
@@ -408,10 +486,12 @@ int upload_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t n, i
     const SeqSet& Y = yset(c);
     int mr = 0, mc = 0;
     long long cc = 0;
+    c->h_la.resize((size_t)n); c->h_lb.resize((size_t)n);
     for (int64_t k = 0; k < n; ++k) {
         if (px[k] < 0 || px[k] >= X.n || py[k] < 0 || py[k] >= Y.n)
             return fail(TAXI_E_ARG, "pair %lld = (%d, %d) outside the loaded sets", (long long)k, px[k], py[k]);
         const int la = (int)(X.off[px[k] + 1] - X.off[px[k]]), lb = (int)(Y.off[py[k] + 1] - Y.off[py[k]]);
+        c->h_la[(size_t)k] = la; c->h_lb[(size_t)k] = lb;
         if (need_nonempty && (la == 0 || lb == 0))
             return fail(TAXI_E_EMPTY, "sequence has zero length (pair %lld)", (long long)k);
         mr = std::max(mr, la); mc = std::max(mc, lb);
@@ -480,7 +560,9 @@ int taxi_ctx_create(int device, taxi_ctx** out)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
-    if (e != cudaSuccess) { delete c; return fail(TAXI_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = c->status.reserve(1);
+    if (e == cudaSuccess) e = cudaMemset(c->status.p, 0, sizeof(int));
+    if (e != cudaSuccess) { taxi_ctx_destroy(c); return fail(TAXI_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return TAXI_OK;
 }
@@ -493,9 +575,9 @@ void taxi_ctx_destroy(taxi_ctx* c)
     for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); }
     c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
-    c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
+    c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_units.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
-    c->d_argidx.release(); c->d_argval.release();
+    c->d_argidx.release(); c->d_argval.release(); c->d_bestcounts.release(); c->d_bestmetrics.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -675,7 +757,7 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
         for (int k = 0; k < K + M; ++k) groups += !rows[k].empty();
         Fast16 f16{};
         int H = 0, mode = 0;
-        if (groups > 1 && !c->force_general && fast16_eligible(c, std::min(mr, 32 * 32 - 1), mc, &f16, &H, &mode)) {
+        if (groups > 1 && !c->force_general && fast16_eligible(c, std::min(mr, 32 * 32 - 1), mc, 0, &f16, &H, &mode)) {
             std::vector<int32_t> all;
             all.reserve((size_t)nx);
             for (int k = K + M - 1; k >= 0; --k) {   // the expensive groups first
@@ -775,9 +857,9 @@ int taxi_alignment_capacity(taxi_ctx* c, const int32_t* px, const int32_t* py, i
     return TAXI_OK;
 }
 
-int taxi_align_strings(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs,
-                       const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
-                       int32_t* out_score)
+int taxi_align_strings_metrics(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs,
+                               const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
+                               uint32_t flags, int32_t* out_score, int32_t* out_counts, double* out_metrics)
 {
     int rc = check_ctx(c, true);
     if (rc) return rc;
@@ -795,20 +877,33 @@ int taxi_align_strings(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_
     CUDA_TRY(c->d_alny.reserve((size_t)total + 16));
     CUDA_TRY(c->d_alnoff.reserve((size_t)npairs + 1));
     CUDA_TRY(c->d_alnstart.reserve((size_t)npairs));
-    CUDA_TRY(c->d_score.reserve((size_t)npairs));
+    if (!out_score) flags &= ~(uint32_t)TAXI_OUT_SCORE;
+    if (!out_counts) flags &= ~(uint32_t)TAXI_OUT_COUNTS;
+    if (!out_metrics) flags &= ~(uint32_t)TAXI_OUT_METRICS;
+    if ((rc = reserve_outputs(c, npairs, flags))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->d_alnoff.p, aln_offsets, ((size_t)npairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     AlignArgs a{};
     fill_rect(a, c, 0, 0, 1, npairs);
     a.px = c->d_px.p; a.py = c->d_py.p;
-    a.score = c->d_score.p;
+    a.score = (flags & TAXI_OUT_SCORE) ? c->d_score.p : nullptr;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? c->d_counts.p : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? c->d_metrics.p : nullptr;
     a.aln_x = c->d_alnx.p; a.aln_y = c->d_alny.p; a.aln_off = c->d_alnoff.p; a.aln_start = c->d_alnstart.p;
     c->cells += cells;
     if ((rc = enqueue_align(c, a, mr, mc))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_x, c->d_alnx.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(out_y, c->d_alny.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(aln_start, c->d_alnstart.p, (size_t)npairs * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    if (out_score) CUDA_TRY(cudaMemcpyAsync(out_score, c->d_score.p, (size_t)npairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = download_outputs(c, npairs, flags, out_score, out_counts, out_metrics))) return rc;
     return finish_align(c);
+}
+
+int taxi_align_strings(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t npairs,
+                       const int64_t* aln_offsets, uint8_t* out_x, uint8_t* out_y, int64_t* aln_start,
+                       int32_t* out_score)
+{
+    return taxi_align_strings_metrics(c, px, py, npairs, aln_offsets, out_x, out_y, aln_start,
+                                      out_score ? TAXI_OUT_SCORE : 0u, out_score, nullptr, nullptr);
 }
 
 static int enqueue_count(taxi_ctx* c, CountArgs a)
@@ -817,8 +912,6 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
     const SeqSet& Y = yset(c);
     a.x = Planes{X.planes.p, X.W, X.n};
     a.y = Planes{Y.planes.p, Y.W, Y.n};
-    CUDA_TRY(c->status.reserve(1));
-    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     if (a.px) {
         const long long blocks = (a.npairs + 255) / 256;
@@ -922,11 +1015,49 @@ int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, in
     return TAXI_OK;
 }
 
+int taxi_best_rows(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, int32_t metric, int32_t align,
+                   int32_t* out_index, double* out_metrics, int32_t* out_counts)
+{
+    int rc = check_ctx(c, align != 0);
+    if (rc) return rc;
+    reset_stats(c);
+    if (metric < 0 || metric > 3 || !out_index) return fail(TAXI_E_ARG, "bad argument");
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    if (nx == 0) return TAXI_OK;
+    if (ny == 0) return fail(TAXI_E_ARG, "no columns to reduce over");
+    if (ny > kChunkPairs) return fail(TAXI_E_ARG, "too many columns for one device block (%d > %lld)", ny, kChunkPairs);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    const uint32_t flags = TAXI_OUT_COUNTS | TAXI_OUT_METRICS;
+    if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
+    CUDA_TRY(c->d_argidx.reserve((size_t)rows));
+    CUDA_TRY(c->d_bestmetrics.reserve((size_t)rows * 4));
+    CUDA_TRY(c->d_bestcounts.reserve((size_t)rows * 4));
+    for (int32_t r0 = 0; r0 < nx; r0 += rows) {
+        const int32_t nr = std::min(rows, nx - r0);
+        if (align) rc = taxi_align_rect_device(c, x0 + r0, nr, y0, ny, flags, nullptr, c->d_counts.p, c->d_metrics.p);
+        else rc = taxi_count_rect_device(c, x0 + r0, nr, y0, ny, flags, c->d_counts.p, c->d_metrics.p);
+        if (rc) return rc;
+        const int wpb = 8;
+        best_rows_kernel<<<(nr + wpb - 1) / wpb, wpb * 32, 0, c->stream>>>(c->d_metrics.p, c->d_counts.p, nr, ny, metric, y0,
+                                                                            c->d_argidx.p, c->d_bestmetrics.p, c->d_bestcounts.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(out_index + r0, c->d_argidx.p, (size_t)nr * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (out_metrics)
+            CUDA_TRY(cudaMemcpyAsync(out_metrics + 4 * (size_t)r0, c->d_bestmetrics.p, (size_t)nr * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (out_counts)
+            CUDA_TRY(cudaMemcpyAsync(out_counts + 4 * (size_t)r0, c->d_bestcounts.p, (size_t)nr * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = finish_align(c))) return rc;
+    }
+    return TAXI_OK;
+}
+
 void* taxi_host_alloc(int64_t bytes)
 {
     void* p = nullptr;
     if (bytes <= 0) return nullptr;
-    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail(TAXI_E_NOMEM, "cudaHostAlloc(%lld) failed", (long long)bytes); return nullptr; }
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail(TAXI_E_NOMEM, "cudaHostAlloc(%lld) failed", (long long)bytes); return nullptr; }
     return p;
 }
 

@@ -147,9 +147,11 @@ class Engine:
         N.check(self._lib.taxi_align_pairs(self._ctx, _p(px), _p(py), len(px), flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, None)
 
-    def align_strings_raw(self, px, py) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
-        """-> (aln_x, aln_y, start, off, scores): pair k's gapped strings are aln_x / aln_y[start[k]:off[k + 1]]
-        (right-aligned in slots of len(x) + len(y) bytes)."""
+    def align_strings_raw(self, px, py, want=("score",)) -> tuple:
+        """-> (aln_x, aln_y, start, off, scores[, result dict]): pair k's gapped strings are
+        aln_x / aln_y[start[k]:off[k + 1]] (right-aligned in slots of len(x) + len(y) bytes).
+        With "counts" / "metrics" in `want` the same launch also fills them (sixth element: the
+        dict align_pairs would return), so strings and distances come from ONE alignment."""
         px = np.ascontiguousarray(px, dtype=np.int32)
         py = np.ascontiguousarray(py, dtype=np.int32)
         n = len(px)
@@ -159,9 +161,12 @@ class Engine:
         ox = np.zeros(max(total, 1), dtype=np.uint8)
         oy = np.zeros(max(total, 1), dtype=np.uint8)
         start = np.zeros(max(n, 1), dtype=np.int64)
-        score = np.zeros(max(n, 1), dtype=np.int32)
-        N.check(self._lib.taxi_align_strings(self._ctx, _p(px), _p(py), n, _p(off), _p(ox), _p(oy), _p(start), _p(score)))
-        return ox, oy, start, off, score[:n]
+        flags, score, counts, metrics = self._outputs(n, tuple(want) + ("score",))
+        N.check(self._lib.taxi_align_strings_metrics(self._ctx, _p(px), _p(py), n, _p(off), _p(ox), _p(oy), _p(start),
+                                                     flags, _p(score), _p(counts), _p(metrics)))
+        if counts is None and metrics is None:
+            return ox, oy, start, off, score
+        return ox, oy, start, off, score, self._result(score, counts, metrics, None)
 
     def align_strings(self, px, py) -> tuple[list[bytes], list[bytes], np.ndarray]:
         """-> (aligned x, aligned y, scores) for each pair, Biopython's first alignment."""

@@ -92,17 +92,22 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
     rows = max(1, max_pairs // max(ny, 1))
     for x0 in range(0, len(xs), rows):
         nx = min(rows, len(xs) - x0)
-        if align:
+        aligned = aligned_raw = None
+        if align and want_strings:
+            # one launch feeds both the distance files and aligned_pairs.txt (the reference aligns
+            # each pair once, versus_all.py:527-552)
+            px, py = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
+            px, py = (px + x0).astype(np.int32), py.astype(np.int32)
+            ox, oy, start, off, _, res = engine.align_strings_raw(px, py, want=("metrics",))
+            metrics = res["metrics"].reshape(nx, ny, 4)
+            if raw_strings:
+                aligned_raw = (ox, oy, start, off)
+            else:
+                bx, by = ox.tobytes(), oy.tobytes()
+                aligned = [(bx[int(start[k]): int(off[k + 1])].decode("latin-1"), by[int(start[k]): int(off[k + 1])].decode("latin-1"))
+                           for k in range(nx * ny)]
+        elif align:
             metrics = engine.align_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
         else:
             metrics = engine.count_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
-        aligned = aligned_raw = None
-        if align and want_strings:
-            px, py = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
-            px, py = (px + x0).astype(np.int32), py.astype(np.int32)
-            if raw_strings:
-                aligned_raw = engine.align_strings_raw(px, py)[:4]
-            else:
-                ax, ay, _ = engine.align_strings(px, py)
-                aligned = [(a.decode("latin-1"), b.decode("latin-1")) for a, b in zip(ax, ay)]
         yield PairBlock(x0, nx, metrics, aligned, aligned_raw)

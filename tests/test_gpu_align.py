@@ -144,6 +144,94 @@ def test_mixed_lengths_in_one_warp(engine):
     check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
 
 
+def _fragments(rng, n, ylen, xlens, sub=0.04):
+    """x = a slightly mutated fragment of y cut at a random offset (so y overhangs x on both sides:
+    the leading end gap is long), with the given x lengths in turn."""
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    xs, ys = [], []
+    for k in range(n):
+        y = al[rng.integers(0, 4, ylen)]
+        la = xlens[k % len(xlens)]
+        o = int(rng.integers(0, ylen - la + 1)) if la < ylen else 0
+        x = y[o:o + la].copy()
+        hit = rng.random(len(x)) < sub
+        x[hit] = al[rng.integers(0, 4, int(hit.sum()))]
+        xs.append(x.tobytes()); ys.append(y.tobytes())
+    return xs, ys
+
+
+def test_fragment_next_to_a_longer_neighbour(engine):
+    """The two pairs of a warp unit of the packed kernel with DIFFERENT x lengths, the shorter x a
+    fragment of a longer y (a long leading end gap): the shorter pair's surplus row slots are dead
+    and must stay inside the dead band however many there are (round-1 advisor finding: they
+    decayed below zero, wrapped, and fed the pair's row 0 a nearly free entry point).  Two-pair
+    launches force the two lengths into one unit, in both halves."""
+    rng = np.random.default_rng(450)
+    scores = (1, -1, -8, -1, -1, -1)
+    for short, longer in [(450, 490), (450, 520), (450, 560), (450, 600), (300, 650), (200, 640), (90, 650), (5, 600)]:
+        xs, ys = _fragments(rng, 2, 650, [short, longer])
+        check_pairs(engine, xs, ys, scores, expect_fast=True)
+        check_pairs(engine, xs[::-1], ys[::-1], scores, expect_fast=True)
+    # a whole list of fragments of every length: units are formed by length, longest first
+    xs, ys = _fragments(rng, 90, 650, list(range(40, 651, 7)))
+    check_pairs(engine, xs, ys, scores, expect_fast=True)
+    xs, ys = _fragments(rng, 31, 1500, [300, 1500, 700, 1100, 1024, 1023, 520])   # several stripes
+    check_pairs(engine, xs, ys, scores, strings=False, expect_fast=True)
+    # other eligible score sets, short rows-per-lane variants
+    for sc in [(2, -1, -3, -2, -1, -1), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2)]:
+        xs, ys = _fragments(rng, 40, 250, [30, 250, 90, 200, 140, 60], sub=0.1)
+        check_pairs(engine, xs, ys, sc, expect_fast=True)
+
+
+@pytest.mark.parametrize("ny", [1, 3, 5, 8])
+def test_rectangle_rows_of_different_length_odd_width(engine, ny):
+    """Rectangles whose width is odd: a warp unit never straddles two rows (rows of different
+    length would share it), the last unit of a row holds a single pair."""
+    rng = np.random.default_rng(31 + ny)
+    xs, ys = _fragments(rng, 14, 650, [450, 560, 300, 650, 520, 90, 600])
+    ys = ys[:ny]
+    px, py = np.divmod(np.arange(len(xs) * ny), ny)
+    want = oracle_batch(xs, ys, px, py, None)
+    engine.set_scores(None)
+    for force_general, force_top, sort_columns in ((0, 0, 1), (0, 0, 0), (0, 1, 1), (1, 0, 1)):
+        engine.set_option("force_general", force_general)
+        engine.set_option("force_top", force_top)
+        engine.set_option("sort_columns", sort_columns)
+        try:
+            engine.load(xs, 0)
+            engine.load(ys, 1)
+            got = engine.align_rect(0, len(xs), 0, ny)
+        finally:
+            engine.set_option("force_general", 0)
+            engine.set_option("force_top", 0)
+            engine.set_option("sort_columns", 1)
+        assert np.array_equal(got["score"].ravel(), want["score"]), (force_general, force_top, sort_columns)
+        assert np.array_equal(got["counts"].reshape(-1, 4), want["counts"])
+        assert_metrics_close(got["metrics"].reshape(-1, 4), want["metrics"])
+
+
+def test_strings_and_metrics_from_one_launch(engine):
+    """taxi_align_strings_metrics: gapped strings, scores, counts and metrics of the same alignment
+    in one launch, equal to the two separate calls."""
+    rng = np.random.default_rng(77)
+    xs, ys = random_pairs(rng, 75, 30, 400, sub=0.15, indel=0.04)
+    engine.set_scores(None)
+    engine.load(xs, 0)
+    engine.load(ys, 1)
+    px = np.arange(len(xs), dtype=np.int32)
+    ox, oy, start, off, score, res = engine.align_strings_raw(px, px, want=("counts", "metrics"))
+    sep = engine.align_pairs(px, px)
+    ax, ay, sc = engine.align_strings(px, px)
+    assert np.array_equal(score, sep["score"]) and np.array_equal(sc, score)
+    assert np.array_equal(res["counts"], sep["counts"])
+    assert np.array_equal(res["metrics"], sep["metrics"], equal_nan=True)
+    bx, by = ox.tobytes(), oy.tobytes()
+    for k in range(len(xs)):
+        assert bx[int(start[k]):int(off[k + 1])] == ax[k] and by[int(start[k]):int(off[k + 1])] == ay[k]
+        c = oracle.count(ax[k].decode(), ay[k].decode()) or (0, 0, 0, 0)
+        assert tuple(res["counts"][k]) == tuple(c)
+
+
 def test_extra_symbols(engine):
     """IUPAC symbols: up to seven distinct symbols stay on the fast path, more fall back."""
     rng = np.random.default_rng(5)
