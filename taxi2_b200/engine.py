@@ -132,13 +132,19 @@ class Engine:
         return self.n[0] if getattr(self, "_y_is_x", True) else self.n[1]
 
     # -- aligned path ------------------------------------------------------------------------
-    def align_rect(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics"), pinned: bool = False) -> dict:
+    def align_rect(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics"), pinned: bool = False,
+                   slot: int = 0, out: dict | None = None) -> dict:
         """pinned=True reuses page-locked result buffers owned by the engine: the returned arrays are
-        views that the next pinned call overwrites."""
+        views that the next pinned call with the same `slot` overwrites.  out = {"score" / "counts" /
+        "metrics": C-contiguous array of nx*ny entries} makes the library write straight into the
+        caller's arrays (e.g. this rectangle's slice of one pinned matrix shared by several GPUs)."""
         npairs = nx * ny
-        flags, score, counts, metrics = self._outputs(npairs, want, self._pinned_pool if pinned else None)
+        flags, score, counts, metrics = self._outputs(npairs, want, self._pool(slot) if pinned else None, out)
         N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, (nx, ny))
+
+    def _pool(self, slot: int) -> dict:
+        return self._pinned_pool.setdefault(int(slot), {})
 
     def align_pairs(self, px, py, want=("score", "counts", "metrics")) -> dict:
         px = np.ascontiguousarray(px, dtype=np.int32)
@@ -184,8 +190,9 @@ class Engine:
                                                  C.c_void_p(d_score), C.c_void_p(d_counts), C.c_void_p(d_metrics)))
 
     # -- alignment-free path -----------------------------------------------------------------
-    def count_rect(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics")) -> dict:
-        flags, _, counts, metrics = self._outputs(nx * ny, want)
+    def count_rect(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics"), pinned: bool = False,
+                   slot: int = 0, out: dict | None = None) -> dict:
+        flags, _, counts, metrics = self._outputs(nx * ny, want, self._pool(slot) if pinned else None, out)
         N.check(self._lib.taxi_count_rect(self._ctx, x0, nx, y0, ny, flags, _p(counts), _p(metrics)))
         return self._result(None, counts, metrics, (nx, ny))
 
@@ -215,38 +222,20 @@ class Engine:
         bottom-aligned in several stripes); 48 = a rectangle whose rows were split into several launches."""
         return int(self._lib.taxi_last_kernel(self._ctx))
 
-    def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None) -> dict:
-        """versusReference at scale (BASELINE config C4): for every row sequence of set 0 the FIRST
-        minimum of metric column `metric` over all of set 1 (versus_reference.py:184-188), plus all
-        four metrics and the counts of that winning pair.  The nx x ny matrix never leaves the
-        device: row tiles are aligned into a device buffer, reduced by the argmin kernel, and only
-        the winners come back.  index = -1 where a query has no defined distance."""
-        import torch
-
-        nx, ny = self.n[0], self.ny
-        if rows_per_tile is None:
-            rows_per_tile = max(1, min(nx, (1 << 22) // max(ny, 1)))
-        dev = torch.device("cuda", self.device)
-        d_metrics = torch.empty((rows_per_tile * ny, 4), dtype=torch.float64, device=dev)
-        d_counts = torch.empty((rows_per_tile * ny, 4), dtype=torch.int32, device=dev)
-        index = np.full(nx, -1, dtype=np.int32)
-        best = np.full((nx, 4), np.nan, dtype=np.float64)
-        counts = np.zeros((nx, 4), dtype=np.int32)
-        for x0 in range(0, nx, rows_per_tile):
-            rows = min(rows_per_tile, nx - x0)
-            if align:
-                self.align_rect_device(x0, rows, 0, ny, 0, d_counts.data_ptr(), d_metrics.data_ptr())
-            else:
-                self.count_rect_device(x0, rows, 0, ny, d_counts.data_ptr(), d_metrics.data_ptr())
-            self.sync()
-            idx, _ = self.argmin_rows_device(d_metrics.data_ptr(), rows, ny, metric)
-            index[x0:x0 + rows] = idx
-            ok = np.nonzero(idx >= 0)[0]
-            if len(ok):
-                flat = torch.from_numpy((ok.astype(np.int64) * ny + idx[ok].astype(np.int64))).to(dev)
-                best[x0 + ok] = d_metrics.index_select(0, flat).cpu().numpy()
-                counts[x0 + ok] = d_counts.index_select(0, flat).cpu().numpy()
+    def best_rows(self, x0: int, nx: int, y0: int, ny: int, metric: int = 0, align: bool = True) -> dict:
+        """Best match of every row x0..x0+nx over the columns [y0, y0+ny): first minimum of metric
+        column `metric` (versus_reference.py:184-188) with all four metrics and the counts of the
+        winning pair.  The nx x ny matrix never leaves the device (taxi_best_rows).
+        index = -1 where a row has no defined distance."""
+        index = np.full(max(nx, 1), -1, dtype=np.int32)[:nx]
+        best = np.full((max(nx, 1), 4), np.nan, dtype=np.float64)[:nx]
+        counts = np.zeros((max(nx, 1), 4), dtype=np.int32)[:nx]
+        N.check(self._lib.taxi_best_rows(self._ctx, x0, nx, y0, ny, int(metric), int(bool(align)), _p(index), _p(best), _p(counts)))
         return dict(index=index, metrics=best, counts=counts)
+
+    def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None) -> dict:
+        """versusReference at scale (BASELINE config C4): best_rows over all of set 0 x all of set 1."""
+        return self.best_rows(0, self.n[0], 0, self.ny, metric, align)
 
     def sync(self) -> None:
         N.check(self._lib.taxi_sync(self._ctx))
@@ -258,8 +247,13 @@ class Engine:
 
     # -- helpers -----------------------------------------------------------------------------
     @staticmethod
-    def _outputs(n: int, want: Seq[str], pool: dict | None = None):
+    def _outputs(n: int, want: Seq[str], pool: dict | None = None, out: dict | None = None):
         def buffer(key, shape, dtype):
+            if out is not None and key in out:
+                given = out[key]
+                if given.dtype != np.dtype(dtype) or not given.flags.c_contiguous or given.size != int(np.prod(shape)):
+                    raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of {int(np.prod(shape))} elements")
+                return given.reshape(shape)
             if pool is None:
                 return np.zeros(shape, dtype=dtype)
             held = pool.get(key)

@@ -69,16 +69,57 @@ class PairBlock(NamedTuple):
     metrics: np.ndarray          # (nx, ny, 4) float64, NaN = undefined
     aligned: list | None         # nx*ny (aligned_x, aligned_y) strings, or None
     aligned_raw: tuple | None = None   # (aln_x, aln_y, start, off) arrays of Engine.align_strings_raw, or None
+    extra: object = None         # whatever the caller's `extra(engine, block)` returned (computed on the block's GPU thread)
+
+
+_multi_engines: dict = {}
+
+# pairs per device block of iter_pair_blocks (whole rows); tests shrink it to force many blocks
+MAX_BLOCK_PAIRS = 1 << 20
+
+
+def task_engine(task):
+    """The process-wide MultiEngine for a task's device selection: `task.devices` (a list of CUDA
+    device indices, or "all") when set, else the single `task.device`.  One context + one host
+    thread per GPU (taxi2_b200/multi.py); raises without a GPU -- there is no CPU path."""
+    from ..multi import MultiEngine
+
+    devices = getattr(task, "devices", None)
+    if devices == "all":
+        key = "all"
+        devices = None
+    elif devices:
+        key = tuple(int(d) for d in devices)
+        devices = list(key)
+    else:
+        key = (int(task.device),)
+        devices = list(key)
+    eng = _multi_engines.get(key)
+    if eng is None:
+        eng = _multi_engines[key] = MultiEngine(devices)
+    return eng
 
 
 def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, align: bool, want_strings: bool,
-                     scores, max_pairs: int = 1 << 20, raw_strings: bool = False):
-    """Drive the device over the row-major product xs x ys (ys=None: xs x xs) in blocks of whole
-    rows, yielding PairBlock in reference order.  One launch per block (plus one for strings).
-    raw_strings: hand the gapped strings over as the library's arrays (for the native pair writer)
-    instead of one Python string per sequence."""
-    from ..engine import scores_vector
+                     scores, max_pairs: int | None = None, raw_strings: bool = False, extra=None):
+    """Drive the device(s) over the row-major product xs x ys (ys=None: xs x xs) in blocks of whole
+    rows, yielding PairBlock in reference order.  One launch per block: gapped strings and
+    distances come from the same alignment (the reference aligns each pair once,
+    versus_all.py:527-552).
 
+    `engine` is a MultiEngine (or a single Engine, wrapped): blocks are dealt to the GPUs by the
+    static LPT plan and computed ahead of the consumer (two finished blocks per GPU at most), so
+    the caller's formatting / writing of block k overlaps the alignment of the next blocks.
+    raw_strings: hand the gapped strings over as the library's arrays (for the native pair writer)
+    instead of one Python string per sequence.  extra(engine, block): optional per-block work that
+    needs the block's own context (runs on its GPU thread); its result is block.extra."""
+    from ..engine import Engine, scores_vector
+    from ..multi import MultiEngine
+
+    if isinstance(engine, Engine):
+        single = engine
+        engine = MultiEngine.__new__(MultiEngine)
+        engine.devices, engine.engines, engine.lens = [single.device], [single], [None, None]
     same_set = ys is None
     ylist = xs if same_set else ys
     if align:
@@ -87,18 +128,20 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
     if not same_set:
         engine.load([s.seq for s in ylist], 1)
     ny = len(ylist)
+    if max_pairs is None:
+        max_pairs = MAX_BLOCK_PAIRS
     if align and want_strings:
         max_pairs = min(max_pairs, 1 << 18)   # ~1.3 KB of gapped strings per barcode pair, twice
     rows = max(1, max_pairs // max(ny, 1))
-    for x0 in range(0, len(xs), rows):
-        nx = min(rows, len(xs) - x0)
+    tiles = engine.row_tiles(rows)
+
+    def compute(eng, tile, slot) -> PairBlock:
+        x0, nx = tile.x0, tile.nx
         aligned = aligned_raw = None
         if align and want_strings:
-            # one launch feeds both the distance files and aligned_pairs.txt (the reference aligns
-            # each pair once, versus_all.py:527-552)
             px, py = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
             px, py = (px + x0).astype(np.int32), py.astype(np.int32)
-            ox, oy, start, off, _, res = engine.align_strings_raw(px, py, want=("metrics",))
+            ox, oy, start, off, _, res = eng.align_strings_raw(px, py, want=("metrics",))
             metrics = res["metrics"].reshape(nx, ny, 4)
             if raw_strings:
                 aligned_raw = (ox, oy, start, off)
@@ -107,7 +150,13 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
                 aligned = [(bx[int(start[k]): int(off[k + 1])].decode("latin-1"), by[int(start[k]): int(off[k + 1])].decode("latin-1"))
                            for k in range(nx * ny)]
         elif align:
-            metrics = engine.align_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
+            metrics = eng.align_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
         else:
-            metrics = engine.count_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
-        yield PairBlock(x0, nx, metrics, aligned, aligned_raw)
+            metrics = eng.count_rect(x0, nx, 0, ny, want=("metrics",))["metrics"]
+        block = PairBlock(x0, nx, metrics, aligned, aligned_raw)
+        if extra is not None:
+            block = block._replace(extra=extra(eng, block))
+        return block
+
+    for _, block in engine.run_tiles(tiles, compute, depth=2, ordered=True):
+        yield block

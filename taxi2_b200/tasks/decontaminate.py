@@ -24,7 +24,7 @@ from ..handlers import FileHandler
 from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, Sequences
 from ..types import AttrDict
-from .common import Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none
+from .common import Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none, task_engine
 from .dereplicate import output_handler
 
 
@@ -35,6 +35,7 @@ class _DecontaminateBase:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.devices = None   # list of CUDA device indices or "all": shard the pair product over several GPUs
         self.native_writers: bool = True   # batch writers and row minima without per-pair Python (same bytes)
         self.input: Sequences = None
         self.outgroup: Sequences = None
@@ -54,15 +55,13 @@ class _DecontaminateBase:
     def _minimums(self, data, group, pairs_path, linear_path, matrix_path, scale: float):
         """Per-query minimum Distance of data x group, writing the pair / distance files on the way
         (generator over queries, in order)."""
-        from ..engine import default_engine
-
         p = self.params
         metric = p.distances.metric
         (col,) = metric_columns([metric])
         fmt, missing = p.format.float, p.format.missing
         xs = list(data.normalize() if p.pairs.align else data)
         ys = list(group.normalize() if p.pairs.align else group)
-        engine = default_engine(self.device)
+        engine = task_engine(self)
         writers = []
         pairs_file = linear_file = matrix_file = None
         if p.pairs.align and p.pairs.write:

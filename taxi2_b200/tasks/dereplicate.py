@@ -23,7 +23,7 @@ from ..handlers import FileHandler
 from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, SequenceHandler, Sequences
 from ..types import AttrDict
-from .common import Results, console_report, create_parents, metric_columns, number_or_none
+from .common import Results, console_report, create_parents, metric_columns, number_or_none, task_engine
 
 
 class AllInfo(NamedTuple):
@@ -64,6 +64,7 @@ class Dereplicate:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.devices = None   # list of CUDA device indices or "all": shard the pair product over several GPUs
 
         self.input: Sequences = None
         self.output_format: FileFormat = None
@@ -95,7 +96,7 @@ class Dereplicate:
         self.paths.distances_matricial = w / "distances" / f"{metric}.matricial.tsv"
 
     def start(self) -> Results:
-        from ..engine import default_engine, scores_vector
+        from ..engine import scores_vector
 
         ts = perf_counter()
         self.excluded = set()
@@ -111,7 +112,7 @@ class Dereplicate:
         data = [s for s in self.input if len(s.seq) >= p.thresholds.length]   # raw strings, gaps included
         work = [s.normalize() for s in data] if p.pairs.align else data
         n = len(data)
-        engine = default_engine(self.device)
+        engine = task_engine(self).engines[0]
         if p.pairs.align:
             engine.set_scores(scores_vector(dict(p.pairs.scores)) if p.pairs.scores is not None else None)
         engine.load([s.seq for s in work], 0)

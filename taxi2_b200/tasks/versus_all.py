@@ -23,7 +23,7 @@ from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, Sequences
 from ..statistics import StatisticsCalculator, StatisticsHandler
 from ..types import AttrDict
-from .common import ComparisonType, Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none
+from .common import ComparisonType, Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none, task_engine
 
 
 class SimpleAggregator:
@@ -107,6 +107,7 @@ class VersusAll:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.devices = None   # list of CUDA device indices or "all": shard the pair product over several GPUs
         self.native_writers: bool = True   # batch formatter for plain float formats (same bytes as the handlers)
 
         self.input = AttrDict()
@@ -169,8 +170,6 @@ class VersusAll:
 
     # -- the run -----------------------------------------------------------------------------------
     def start(self) -> Results:
-        from ..engine import default_engine
-
         ts = perf_counter()
         self.generate_paths()
         self.check_metrics()
@@ -182,7 +181,7 @@ class VersusAll:
 
         sequences = list(self.input.sequences.normalize() if p.pairs.align else self.input.sequences)
         n = len(sequences)
-        engine = default_engine(self.device)
+        engine = task_engine(self)
         self.write_statistics(sequences)
 
         writers = []
@@ -219,8 +218,9 @@ class VersusAll:
         same_key = duplicate_groups(sequences)
         try:
             for block in iter_pair_blocks(engine, sequences, None, p.pairs.align, pairs_file is not None or native_pairs is not None,
-                                          p.pairs.scores, raw_strings=native_pairs is not None):
-                undefined = self._undefined_mask(engine, block, sequences, same_key, p.pairs.align)
+                                          p.pairs.scores, raw_strings=native_pairs is not None,
+                                          extra=lambda eng, blk: self._undefined_mask(eng, blk, sequences, same_key, p.pairs.align)):
+                undefined = block.extra
                 if native_pairs is not None:
                     ids, first = native_pairs
                     fastwrite.format_aligned_pairs(self.paths.aligned_pairs, first, ids, ids, block.x0, block.nx, n, *block.aligned_raw)

@@ -20,7 +20,7 @@ from ..distances import Distance, DistanceHandler, DistanceMetric
 from ..pairs import SequencePair, SequencePairHandler
 from ..sequences import Sequence, Sequences
 from ..types import AttrDict
-from .common import Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none
+from .common import Results, console_report, create_parents, iter_pair_blocks, metric_columns, number_or_none, task_engine
 
 
 class VersusReference:
@@ -30,6 +30,7 @@ class VersusReference:
         self.progress_handler: Callable = console_report
         self.progress_interval: float = 0.015
         self.device: int = 0
+        self.devices = None   # list of CUDA device indices or "all": shard the pair product over several GPUs
         self.native_writers: bool = True   # batch formatter for plain float formats (same bytes as the handlers)
 
         self.input = AttrDict()
@@ -59,8 +60,6 @@ class VersusReference:
             d.extra_metrics.remove(d.metric)
 
     def start(self) -> Results:
-        from ..engine import default_engine
-
         ts = perf_counter()
         self.check_metrics()
         self.generate_paths()
@@ -73,7 +72,7 @@ class VersusReference:
         data = list(self.input.data.normalize() if p.pairs.align else self.input.data)
         reference = list(self.input.reference.normalize() if p.pairs.align else self.input.reference)
         nref = len(reference)
-        engine = default_engine(self.device)
+        engine = task_engine(self)
 
         writers = []
         pairs_file = linear_file = matrix_file = None
