@@ -9,6 +9,7 @@ from .oracle import (  # noqa: F401
     align_count_pairs,
     build,
     count,
+    count_pairs,
     max_threads,
     metrics,
     uses_gotoh,

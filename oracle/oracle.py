@@ -48,6 +48,8 @@ def _load():
         lib.taxi_oracle_align_count_pairs.argtypes = [u8p, i64p, i32p, i32p, C.c_int64, f64p, C.c_int32,
                                                       i32p, i32p, f64p, i32p]
         lib.taxi_oracle_align_count_pairs.restype = C.c_int
+        lib.taxi_oracle_count_pairs.argtypes = [u8p, i64p, i32p, i32p, C.c_int64, C.c_int32, i32p, f64p]
+        lib.taxi_oracle_count_pairs.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -126,3 +128,21 @@ def align_count_pairs(seqs: np.ndarray, offsets: np.ndarray, px: np.ndarray, py:
     if rc != 0:
         raise RuntimeError(f"taxi_oracle_align_count_pairs failed: {rc}")
     return dict(score=score, counts=counts, metrics=met, alnlen=alnlen)
+
+
+def count_pairs(seqs: np.ndarray, offsets: np.ndarray, px: np.ndarray, py: np.ndarray, threads: int = 0):
+    """Alignment-free batch (align = False): counts int32[P,4] and metrics float64[P,4] of the raw
+    strings of every pair, truncated to the shorter one (all-zero counts / NaN without overlap)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    px = np.ascontiguousarray(px, dtype=np.int32)
+    py = np.ascontiguousarray(py, dtype=np.int32)
+    P = px.shape[0]
+    counts = np.zeros((P, 4), np.int32)
+    met = np.full((P, 4), np.nan, np.float64)
+    ptr = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    rc = _load().taxi_oracle_count_pairs(ptr(seqs, C.c_uint8), ptr(offsets, C.c_int64), ptr(px, C.c_int32), ptr(py, C.c_int32),
+                                         P, threads, ptr(counts, C.c_int32), ptr(met, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"taxi_oracle_count_pairs failed: {rc}")
+    return dict(counts=counts, metrics=met)

@@ -333,6 +333,52 @@ static void* worker(void* arg)
     return NULL;
 }
 
+/*
+ * Alignment-free mode for a list of pairs (params.pairs.align = False, versus_all.py:522-530):
+ * the four calc.seq_distances_* scans on the raw strings (distances.py:319-348), truncated to the
+ * shorter one.  Same threading as the aligned batch.
+ */
+typedef struct {
+    const uint8_t* seqs; const int64_t* offsets; const int32_t* px; const int32_t* py;
+    int64_t npairs; int32_t* out_counts; double* out_metrics; int64_t next;
+} count_job_t;
+
+static void* count_worker(void* arg)
+{
+    count_job_t* job = (count_job_t*)arg;
+    for (;;) {
+        const int64_t p0 = __atomic_fetch_add(&job->next, (int64_t)256, __ATOMIC_RELAXED);
+        if (p0 >= job->npairs) break;
+        const int64_t p1 = p0 + 256 < job->npairs ? p0 + 256 : job->npairs;
+        for (int64_t p = p0; p < p1; ++p) {
+            const int64_t ox = job->offsets[job->px[p]], oy = job->offsets[job->py[p]];
+            int32_t c[4];
+            taxi_oracle_count(job->seqs + ox, job->offsets[job->px[p] + 1] - ox, job->seqs + oy, job->offsets[job->py[p] + 1] - oy, c);
+            if (job->out_counts) memcpy(job->out_counts + 4 * p, c, sizeof c);
+            if (job->out_metrics) taxi_oracle_metrics(c, job->out_metrics + 4 * p);
+        }
+    }
+    return NULL;
+}
+
+int taxi_oracle_max_threads(void);
+
+int taxi_oracle_count_pairs(const uint8_t* seqs, const int64_t* offsets, const int32_t* px, const int32_t* py,
+                            int64_t npairs, int32_t threads, int32_t* out_counts, double* out_metrics)
+{
+    count_job_t job = { seqs, offsets, px, py, npairs, out_counts, out_metrics, 0 };
+    if (threads <= 0) threads = taxi_oracle_max_threads();
+    if (threads > 256) threads = 256;
+    if (threads == 1) { count_worker(&job); return TAXI_OK; }
+    pthread_t tid[256];
+    int started = 0;
+    for (int t = 0; t < threads; ++t)
+        if (pthread_create(&tid[started], NULL, count_worker, &job) == 0) ++started;
+    if (!started) count_worker(&job);
+    for (int t = 0; t < started; ++t) pthread_join(tid[t], NULL);
+    return TAXI_OK;
+}
+
 int taxi_oracle_max_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);

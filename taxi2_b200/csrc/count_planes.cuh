@@ -5,33 +5,48 @@
 // (reference: src/itaxotools/taxi2/distances.py:319-348, called from versus_all.py:546-552 when
 // versus_all.py:522-530 skipped normalisation and alignment).
 //
-// The packer turns every sequence into four bit planes of 32 columns per word:
-//   b0, b1 : 2-bit nucleotide (A=00 G=01 C=10 T=11; a transition flips only b0)
-//   R      : "real" mask (A/C/G/T)
-//   G      : gap mask ('-')
-// Columns past a sequence's end have R = G = 0, which is exactly "truncate to the shorter".
-// The planes are stored plane-major with the sequence index fastest ([4][W][n]), so a warp whose
-// threads hold consecutive sequences reads every plane word with one coalesced transaction.
+// The packer turns every sequence into four bit planes of 32 columns per word, stored as ONE
+// uint4 per (word, sequence), sequence fastest ([W][n]), so a warp whose threads hold consecutive
+// sequences fetches all four planes of a word with one coalesced 128-bit load:
+//   .x = b0, .y = b1 : 2-bit nucleotide (A=00 G=01 C=10 T=11; a transition flips only b0)
+//   .z = R           : "real" mask (A/C/G/T)
+//   .w = G'          : gap mask ('-'), restricted to the sequence's OWN real span (first..last
+//                      real column).  The distances only look at columns between the first and
+//                      the last column where BOTH sequences are real; a '-' outside a sequence's
+//                      own span can never lie in there, so dropping it at pack time removes the
+//                      leading / trailing pad of pre-aligned rows from the per-pair work.
+// Columns past a sequence's end have R = G' = 0, which is exactly "truncate to the shorter".
+// W is padded to a multiple of COUNT_G words (zero words).
+//
+// Per pair and word: 7 LOP3 build the four column masks (both-real, transversion, transition,
+// gap column).  POPC issues at 16 lanes/clk/SM on sm_100 (tools/int_peak.cu: a quarter of LOP3),
+// so four popcounts per word would bound the kernel; the masks of COUNT_G = 5 consecutive words
+// go through two carry-save adders per quantity first (4 LOP3) and only 3 words are popcounted
+// (weights 1, 2, 2): 10.2 LOP3 + 2.4 POPC + 1.6 IADD per word, the two pipes about balanced.
+// The trim rule needs no per-word bookkeeping: gap columns are counted over the whole row and the
+// few that precede the first / follow the last both-real column are subtracted afterwards by a
+// scan that starts at the first word where both sequences have real columns (normally it looks
+// at one word per end).
 #pragma once
 #include "common.cuh"
 
 namespace taxi {
 
+constexpr int COUNT_G = 5;       // words per carry-save group
+
 struct Planes {
-    const uint32_t* w;   // [4][W][nseq] words (plane-major, sequence fastest): b0, b1, R, G
-    int32_t W;           // words per plane
+    const uint4* w;      // [W][nseq]: (b0, b1, R, G') of 32 columns
+    const int2* span;    // [nseq]: first / last word that holds a real column (first > last: none)
+    int32_t W;           // words per sequence, a multiple of COUNT_G
     int32_t nseq;
-    __device__ __forceinline__ uint32_t at(int plane, int word, int seq) const
-    {
-        return __ldg(w + ((size_t)plane * W + word) * nseq + seq);
-    }
+    __device__ __forceinline__ uint4 at(int word, int seq) const { return __ldg(w + (size_t)word * nseq + seq); }
 };
 
-// one thread per (sequence, word): bytes -> planes.  Consecutive threads take consecutive
-// sequences so the plane words are written coalesced; the byte reads of a warp are scattered, but
-// this kernel runs once per load (O(N*L)) and is not on the O(N^2) path.
+// one thread per (sequence, word): bytes -> raw planes (G still holds every '-').  Consecutive
+// threads take consecutive sequences so the plane words are written coalesced; the byte reads of
+// a warp are scattered, but this runs once per load (O(N*L)) and is not on the O(N^2) path.
 __global__ void pack_planes_kernel(const uint8_t* __restrict__ bytes, const int64_t* __restrict__ off,
-                                   int32_t nseq, int32_t W, uint32_t* __restrict__ out)
+                                   int32_t nseq, int32_t W, uint4* __restrict__ out)
 {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)nseq * W;
@@ -50,9 +65,34 @@ __global__ void pack_planes_kernel(const uint8_t* __restrict__ bytes, const int6
             else if (c == 4) G |= 1u << k;
         }
     }
-    const size_t plane = (size_t)W * nseq;
-    uint32_t* dst = out + (size_t)w * nseq + seq;
-    dst[0] = b0; dst[plane] = b1; dst[2 * plane] = R; dst[3 * plane] = G;
+    out[(size_t)w * nseq + seq] = make_uint4(b0, b1, R, G);
+}
+
+// one thread per sequence: find its real span, clip the gap plane to it, record the span words
+__global__ void clip_gaps_kernel(int32_t nseq, int32_t W, uint4* __restrict__ planes, int2* __restrict__ span)
+{
+    const int seq = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seq >= nseq) return;
+    int first = -1, last = -1;   // columns
+    for (int w = 0; w < W; ++w) {
+        const uint32_t R = planes[(size_t)w * nseq + seq].z;
+        if (R) {
+            if (first < 0) first = w * 32 + __ffs(R) - 1;
+            last = w * 32 + 31 - __clz(R);
+        }
+    }
+    for (int w = 0; w < W; ++w) {
+        uint4* p = planes + (size_t)w * nseq + seq;
+        uint32_t keep = 0;
+        if (first >= 0 && w >= first / 32 && w <= last / 32) {
+            keep = 0xffffffffu;
+            if (w == first / 32) keep &= 0xffffffffu << (first % 32);
+            if (w == last / 32) keep &= 0xffffffffu >> (31 - last % 32);
+        }
+        const uint32_t G = p->w;
+        if ((G & keep) != G) p->w = G & keep;
+    }
+    span[seq] = first < 0 ? make_int2(W, -1) : make_int2(first / 32, last / 32);
 }
 
 struct CountArgs {
@@ -65,84 +105,137 @@ struct CountArgs {
     double* metrics;   // [npairs][4] or nullptr
 };
 
-// running state of one pair's scan (columns in order): the trim-to-first/last-both-real rule
-struct CountState {
-    int same, ts, tv, gapc, pend;
-    bool seen;
-    __device__ __forceinline__ void init() { same = ts = tv = gapc = pend = 0; seen = false; }
-    __device__ __forceinline__ void word(uint32_t x0, uint32_t x1, uint32_t xr, uint32_t xg,
-                                         uint32_t y0, uint32_t y1, uint32_t yr, uint32_t yg)
+// carry-save adder over three bit vectors: s = bit sum, c = carries (weight 2)
+__device__ __forceinline__ void csa(uint32_t& s, uint32_t& c, uint32_t a, uint32_t b, uint32_t d)
+{
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(d));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c) : "r"(a), "r"(b), "r"(d));
+}
+
+// popcount of five mask words with three POPCs: ones += popc(s2); twos += popc(c1) + popc(c2)
+__device__ __forceinline__ void add5(int& ones, int& twos, const uint32_t m[COUNT_G])
+{
+    uint32_t s1, c1, s2, c2;
+    csa(s1, c1, m[0], m[1], m[2]);
+    csa(s2, c2, s1, m[3], m[4]);
+    ones += __popc(s2);
+    twos += __popc(c1) + __popc(c2);
+}
+
+// unweighted partial counts of one pair: value = ones + 2 * twos
+struct CountAcc {
+    int n1, n2, v1, v2, s1, s2, g1, g2;   // both-real, transversions, transitions, gap columns
+    __device__ __forceinline__ void init() { n1 = n2 = v1 = v2 = s1 = s2 = g1 = g2 = 0; }
+    __device__ __forceinline__ void group(const uint4 x[COUNT_G], const uint4 y[COUNT_G])
     {
-        const uint32_t both = xr & yr;
-        const uint32_t gapw = (xg & yr) | (xr & yg);
-        if (both) {
-            const uint32_t d0 = x0 ^ y0, d1 = x1 ^ y1;
-            tv += __popc(both & d1);
-            ts += __popc(both & d0 & ~d1);
-            same += __popc(both & ~(d0 | d1));
-            const int lo = __ffs(both) - 1, hi = 31 - __clz(both);
-            const uint32_t upto_hi = (hi == 31) ? 0xffffffffu : ((2u << hi) - 1u);
-            const uint32_t from_lo = seen ? 0xffffffffu : (0xffffffffu << lo);
-            if (seen) gapc += pend;
-            gapc += __popc(gapw & upto_hi & from_lo);
-            pend = __popc(gapw & ~upto_hi);
-            seen = true;
-        } else {
-            pend += __popc(gapw);
+        uint32_t both[COUNT_G], tv[COUNT_G], ts[COUNT_G], gp[COUNT_G];
+#pragma unroll
+        for (int k = 0; k < COUNT_G; ++k) {
+            const uint32_t d0 = x[k].x ^ y[k].x, d1 = x[k].y ^ y[k].y;
+            both[k] = x[k].z & y[k].z;
+            tv[k] = both[k] & d1;
+            ts[k] = both[k] & d0 & ~d1;
+            gp[k] = (x[k].w & y[k].z) | (x[k].z & y[k].w);
         }
-    }
-    __device__ __forceinline__ void store(const CountArgs& a, long long p) const
-    {
-        if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gapc);
-        if (a.metrics) {
-            double m[4];
-            metrics_from_counts(same, ts, tv, gapc, m);
-            double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
-            dst[0] = make_double2(m[0], m[1]);
-            dst[1] = make_double2(m[2], m[3]);
-        }
+        add5(n1, n2, both);
+        add5(v1, v2, tv);
+        add5(s1, s2, ts);
+        add5(g1, g2, gp);
     }
 };
 
+// Gap columns that lie before the first / after the last both-real column of a pair (they were
+// counted with the rest and do not belong to the distance).  `xat(w)` / `yat(w)` fetch a word.
+template <class FX, class FY>
+__device__ __forceinline__ int gaps_outside_trim(FX xat, FY yat, int2 sx, int2 sy)
+{
+    const int w0 = max(sx.x, sy.x), w1 = min(sx.y, sy.y);   // no both-real column outside [w0, w1]
+    int out = 0;
+    for (int w = w0; w <= w1; ++w) {
+        const uint4 x = xat(w), y = yat(w);
+        const uint32_t both = x.z & y.z, g = (x.w & y.z) | (x.z & y.w);
+        if (both) { out += __popc(g & ((both & (0u - both)) - 1u)); break; }   // below the lowest both-real bit
+        out += __popc(g);
+    }
+    for (int w = w1; w >= w0; --w) {
+        const uint4 x = xat(w), y = yat(w);
+        const uint32_t both = x.z & y.z, g = (x.w & y.z) | (x.z & y.w);
+        if (both) { out += __popc(g & ~(0xffffffffu >> __clz(both))); break; }      // above the highest both-real bit
+        out += __popc(g);
+    }
+    // words < w0 and > w1: one of the two sequences has no real column there, and its clipped gap
+    // plane is empty outside its span, so neither term of the gap mask can be set
+    return out;
+}
+
+__device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int n, int tv, int ts, int gap)
+{
+    const int same = n - tv - ts;
+    if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gap);
+    if (a.metrics) {
+        double m[4];
+        metrics_from_counts(same, ts, tv, gap, m);
+        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
+        dst[0] = make_double2(m[0], m[1]);
+        dst[1] = make_double2(m[2], m[3]);
+    }
+}
+
 // Rectangle mode.  A block owns COUNT_TY consecutive y columns (one per thread) and walks the x
-// rows of its slab in groups of COUNT_RX: the y words of a thread are loaded once per group
-// (coalesced across the warp, plane-major layout) and reused for COUNT_RX pairs whose x words come
-// from shared memory as warp broadcasts.  Results are written coalesced, 16 B + 32 B per pair.
+// rows of its slab in register tiles of COUNT_RX: the y words of a thread are loaded once per
+// tile and word group (coalesced 128-bit loads) and reused for COUNT_RX pairs whose x words come
+// from shared memory as 128-bit warp broadcasts.  Results are written coalesced, 16 B + 32 B per pair.
 constexpr int COUNT_TY = 256;
-constexpr int COUNT_RX = 8;
+constexpr int COUNT_RX = 4;
 constexpr int COUNT_SLAB = 64;   // x rows staged in shared memory per block (fewer when the sequences are long)
 
 __global__ void __launch_bounds__(COUNT_TY, 2) count_rect_kernel(const CountArgs a)
 {
-    extern __shared__ uint32_t xs[];   // [slab][4][W]
+    extern __shared__ uint4 xs[];   // [slab][W]
     const int W = min(a.x.W, a.y.W);
     const int yj = blockIdx.x * COUNT_TY + threadIdx.x;          // column inside the rectangle
     const int xbase = blockIdx.y * a.slab;                       // first row of the slab
     const int rows = min(a.slab, a.nx - xbase);
-    for (int k = threadIdx.x; k < rows * 4 * W; k += COUNT_TY) {
-        const int r = k / (4 * W), pw = k % (4 * W);
-        xs[k] = a.x.at(pw / W, pw % W, a.x0 + xbase + r);
+    for (int k = threadIdx.x; k < rows * W; k += COUNT_TY) {
+        const int r = k / W, w = k % W;
+        xs[k] = a.x.at(w, a.x0 + xbase + r);
     }
     __syncthreads();
     if (yj >= a.ny) return;
     const int ys = a.y0 + yj;
+    const int2 sy = __ldg(a.y.span + ys);
     for (int g = 0; g < rows; g += COUNT_RX) {
-        CountState st[COUNT_RX];
+        CountAcc acc[COUNT_RX];
 #pragma unroll
-        for (int k = 0; k < COUNT_RX; ++k) st[k].init();
-        for (int w = 0; w < W; ++w) {
-            const uint32_t y0 = a.y.at(0, w, ys), y1 = a.y.at(1, w, ys), yr = a.y.at(2, w, ys), yg = a.y.at(3, w, ys);
+        for (int k = 0; k < COUNT_RX; ++k) acc[k].init();
+        for (int w = 0; w < W; w += COUNT_G) {
+            uint4 y[COUNT_G];
+#pragma unroll
+            for (int q = 0; q < COUNT_G; ++q) y[q] = a.y.at(w + q, ys);
 #pragma unroll
             for (int k = 0; k < COUNT_RX; ++k) {
-                if (g + k < rows) {
-                    const uint32_t* xw = xs + (size_t)(g + k) * 4 * W + w;
-                    st[k].word(xw[0], xw[W], xw[2 * W], xw[3 * W], y0, y1, yr, yg);
-                }
+                // rows past the slab's end repeat its last row (discarded below): no branch in the hot loop
+                const uint4* xw = xs + (size_t)min(g + k, rows - 1) * W + w;
+                uint4 x[COUNT_G];
+#pragma unroll
+                for (int q = 0; q < COUNT_G; ++q) x[q] = xw[q];
+                acc[k].group(x, y);
             }
         }
 #pragma unroll
-        for (int k = 0; k < COUNT_RX; ++k)
-            if (g + k < rows) st[k].store(a, (long long)(xbase + g + k) * a.ny + yj);
+        for (int k = 0; k < COUNT_RX; ++k) {
+            if (g + k >= rows) break;
+            const CountAcc& c = acc[k];
+            const int n = c.n1 + 2 * c.n2;
+            int gap = c.g1 + 2 * c.g2;
+            const int row = xbase + g + k;
+            if (n > 0 && gap > 0) {
+                const uint4* xw = xs + (size_t)(g + k) * W;
+                gap -= gaps_outside_trim([&](int w) { return xw[w]; }, [&](int w) { return a.y.at(w, ys); },
+                                         __ldg(a.x.span + a.x0 + row), sy);
+            }
+            store_pair(a, (long long)row * a.ny + yj, n, c.v1 + 2 * c.v2, c.s1 + 2 * c.s2, n > 0 ? gap : 0);
+        }
     }
 }
 
@@ -153,12 +246,23 @@ __global__ void __launch_bounds__(256) count_pairs_kernel(const CountArgs a)
     if (p >= a.npairs) return;
     const int xi = a.px[p], yi = a.py[p];
     const int W = min(a.x.W, a.y.W);
-    CountState st;
-    st.init();
-    for (int w = 0; w < W; ++w)
-        st.word(a.x.at(0, w, xi), a.x.at(1, w, xi), a.x.at(2, w, xi), a.x.at(3, w, xi),
-                a.y.at(0, w, yi), a.y.at(1, w, yi), a.y.at(2, w, yi), a.y.at(3, w, yi));
-    st.store(a, p);
+    CountAcc c;
+    c.init();
+    for (int w = 0; w < W; w += COUNT_G) {
+        uint4 x[COUNT_G], y[COUNT_G];
+#pragma unroll
+        for (int q = 0; q < COUNT_G; ++q) { x[q] = a.x.at(w + q, xi); y[q] = a.y.at(w + q, yi); }
+        c.group(x, y);
+    }
+    const int n = c.n1 + 2 * c.n2;
+    int gap = c.g1 + 2 * c.g2;
+    if (n > 0 && gap > 0) {
+        // spans may reach past the shorter set's width: clamp to the common words
+        int2 sx = __ldg(a.x.span + xi), sy = __ldg(a.y.span + yi);
+        sx.y = min(sx.y, W - 1); sy.y = min(sy.y, W - 1);
+        gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xi); }, [&](int w) { return a.y.at(w, yi); }, sx, sy);
+    }
+    store_pair(a, p, n, c.v1 + 2 * c.v2, c.s1 + 2 * c.s2, n > 0 ? gap : 0);
 }
 
 // versus_reference.py:184-188 / decontaminate.py:258-264: first minimum per query row, NaN skipped.

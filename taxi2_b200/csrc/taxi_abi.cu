@@ -68,7 +68,8 @@ struct SeqSet {
     DevBuf<uint8_t> bytes;          // normalized ASCII (DP kernels compare code points)
     DevBuf<uint8_t> codes;          // 3-bit symbol codes for the packed fast path (valid if ctx->codebook_ok)
     DevBuf<int64_t> d_off;
-    DevBuf<uint32_t> planes;        // [n][4][W]
+    DevBuf<uint4> planes;           // [W][n] (b0, b1, R, G') per 32 columns (count_planes.cuh)
+    DevBuf<int2> span;              // [n] first / last word with a real column
     int32_t W = 0;
 };
 
@@ -572,7 +573,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); }
+    for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); s.span.release(); }
     c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
     c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_units.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
@@ -651,11 +652,14 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
         // a symbol first seen in set 1 extends the book: set 0 was encoded with the older book,
         // which is still right for every symbol set 0 contains
     }
-    s.W = std::max(1, (s.maxlen + 31) / 32);
-    CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * 4 * s.W, 1));
+    s.W = std::max(1, ((s.maxlen + 31) / 32 + COUNT_G - 1) / COUNT_G) * COUNT_G;   // whole carry-save groups
+    CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * s.W, 1));
+    CUDA_TRY(s.span.reserve((size_t)std::max(n, 1), 1));
     if (n > 0) {
         const long long total = (long long)n * s.W;
         pack_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(s.bytes.p, s.d_off.p, n, s.W, s.planes.p);
+        CUDA_TRY(cudaGetLastError());
+        clip_gaps_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, s.W, s.planes.p, s.span.p);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -910,26 +914,39 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
 {
     const SeqSet& X = c->set[0];
     const SeqSet& Y = yset(c);
-    a.x = Planes{X.planes.p, X.W, X.n};
-    a.y = Planes{Y.planes.p, Y.W, Y.n};
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    a.x = Planes{X.planes.p, X.span.p, X.W, X.n};
+    a.y = Planes{Y.planes.p, Y.span.p, Y.W, Y.n};
     if (a.px) {
+        CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
         const long long blocks = (a.npairs + 255) / 256;
         count_pairs_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a);
-    } else {
-        const int W = std::min(X.W, Y.W);
-        // x rows per block: as many as fit ~96 KB of shared memory (two blocks per SM), at most COUNT_SLAB
-        const size_t row_bytes = (size_t)4 * W * sizeof(uint32_t);
-        if (row_bytes > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
-        a.slab = (int32_t)std::max<size_t>(1, std::min<size_t>(COUNT_SLAB, (96 * 1024) / row_bytes));
-        const size_t smem = (size_t)a.slab * row_bytes;
-        CUDA_TRY(cudaFuncSetAttribute(count_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)((a.ny + COUNT_TY - 1) / COUNT_TY), (unsigned)((a.nx + a.slab - 1) / a.slab));
-        count_rect_kernel<<<grid, COUNT_TY, smem, c->stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        c->launches += 1;
+        return TAXI_OK;
     }
-    CUDA_TRY(cudaGetLastError());
+    const int W = std::min(X.W, Y.W);
+    // x rows per block: as many as fit ~96 KB of shared memory (two blocks per SM), at most COUNT_SLAB
+    const size_t row_bytes = (size_t)W * sizeof(uint4);
+    if (row_bytes > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
+    a.slab = (int32_t)std::max<size_t>(1, std::min<size_t>(COUNT_SLAB, (96 * 1024) / row_bytes));
+    const size_t smem = (size_t)a.slab * row_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(count_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // grid.y is limited to 65535 slabs: taller rectangles go in several launches
+    const int32_t rows_per_launch = 65535 * a.slab;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    for (int32_t r0 = 0; r0 < a.nx; r0 += rows_per_launch) {
+        CountArgs part = a;
+        part.x0 = a.x0 + r0;
+        part.nx = std::min(rows_per_launch, a.nx - r0);
+        if (part.counts) part.counts += 4LL * r0 * a.ny;
+        if (part.metrics) part.metrics += 4LL * r0 * a.ny;
+        dim3 grid((unsigned)((a.ny + COUNT_TY - 1) / COUNT_TY), (unsigned)((part.nx + a.slab - 1) / a.slab));
+        count_rect_kernel<<<grid, COUNT_TY, smem, c->stream>>>(part);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 1;
     return TAXI_OK;
 }
 
@@ -941,7 +958,6 @@ int taxi_count_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
-    if ((nx + COUNT_SLAB - 1) / COUNT_SLAB > 65535) return fail(TAXI_E_ARG, "rectangle too tall for one launch (max %d rows)", 65535 * COUNT_SLAB);
     CUDA_TRY(cudaSetDevice(c->device));
     CountArgs a{};
     a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.nx = nx; a.ny = ny; a.npairs = npairs;

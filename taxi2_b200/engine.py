@@ -143,6 +143,16 @@ class Engine:
         N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, (nx, ny))
 
+    def align_rect_resident(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics")) -> None:
+        """Same work with the results left in the library's device buffers (no download): what a
+        caller that reduces on the device needs, and the device-resident leg of bench.py."""
+        flags = sum(f for k, f in (("score", N.OUT_SCORE), ("counts", N.OUT_COUNTS), ("metrics", N.OUT_METRICS)) if k in want)
+        N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, None, None, None))
+
+    def count_rect_resident(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics")) -> None:
+        flags = sum(f for k, f in (("counts", N.OUT_COUNTS), ("metrics", N.OUT_METRICS)) if k in want)
+        N.check(self._lib.taxi_count_rect(self._ctx, x0, nx, y0, ny, flags, None, None))
+
     def _pool(self, slot: int) -> dict:
         return self._pinned_pool.setdefault(int(slot), {})
 
@@ -249,7 +259,7 @@ class Engine:
     @staticmethod
     def _outputs(n: int, want: Seq[str], pool: dict | None = None, out: dict | None = None):
         def buffer(key, shape, dtype):
-            if out is not None and key in out:
+            if out is not None and key in out and n > 0:
                 given = out[key]
                 if given.dtype != np.dtype(dtype) or not given.flags.c_contiguous or given.size != int(np.prod(shape)):
                     raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of {int(np.prod(shape))} elements")

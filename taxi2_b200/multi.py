@@ -175,7 +175,7 @@ class MultiEngine:
                 t.join()
 
     # -- whole-matrix products -------------------------------------------------------------------------
-    def _matrix(self, mode: str, want, rows_per_tile, pinned: bool, x_range=None) -> dict:
+    def _matrix(self, mode: str, want, rows_per_tile, pinned: bool, x_range=None, out: dict | None = None) -> dict:
         tiles = self.row_tiles(rows_per_tile, 1, x_range)
         x0 = tiles[0].x0 if tiles else 0
         nx, ny = sum(t.nx for t in tiles), self.ny
@@ -183,10 +183,17 @@ class MultiEngine:
         if mode == "count":
             want = tuple(w for w in want if w != "score")
         holders = {}
+        given = out
         out = {}
         for key in want:
             shape, dtype = shapes[key]
-            if pinned:
+            if given is not None and key in given:
+                # caller-owned (e.g. one pinned matrix reused between runs): at least nx rows of the right width
+                arr = given[key]
+                if arr.dtype != np.dtype(dtype) or arr.shape[1:] != shape[1:] or arr.shape[0] < nx or not arr.flags.c_contiguous:
+                    raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of shape >= {shape}")
+                out[key] = arr[:nx]
+            elif pinned:
                 holders[key] = PinnedArray(shape, dtype)
                 out[key] = holders[key].array
             else:
@@ -207,15 +214,16 @@ class MultiEngine:
         return out
 
     def align_matrix(self, want=("score", "counts", "metrics"), rows_per_tile: int | None = None, pinned: bool = False,
-                     x_range: tuple[int, int] | None = None) -> dict:
+                     x_range: tuple[int, int] | None = None, out: dict | None = None) -> dict:
         """All ordered pairs set 0 x set 1 (or set 0 x set 0), row-major, gathered on the host:
-        every GPU's D2H copy lands in its tiles' slices of one result array per output."""
-        return self._matrix("align", want, rows_per_tile, pinned, x_range)
+        every GPU's D2H copy lands in its tiles' slices of one result array per output
+        (pinned=True: page-locked arrays owned by the result; out=: the caller's arrays)."""
+        return self._matrix("align", want, rows_per_tile, pinned, x_range, out)
 
     def count_matrix(self, want=("counts", "metrics"), rows_per_tile: int | None = None, pinned: bool = False,
-                     x_range: tuple[int, int] | None = None) -> dict:
+                     x_range: tuple[int, int] | None = None, out: dict | None = None) -> dict:
         """Alignment-free counterpart of align_matrix (params.pairs.align = False)."""
-        return self._matrix("count", want, rows_per_tile, pinned, x_range)
+        return self._matrix("count", want, rows_per_tile, pinned, x_range, out)
 
     def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None, col_tiles: int = 1) -> dict:
         """versusReference at scale (BASELINE config C4): per query of set 0 the FIRST minimum of

@@ -1,11 +1,16 @@
 """Static tile assignment of the pair matrix over the GPUs of one box.
 
-Every pair is independent, so the path shards with NO collective on the compute path: the
-sequence sets are replicated on every GPU (C3: 32 MB), the ordered pair matrix is cut into
-rectangular tiles, tiles are dealt to ranks longest-processing-time-first by DP cells, each rank
-aligns its tiles and writes into its slice of the result.  The only exchange is the final gather
-of per-tile results (or the reduction of per-subset summary statistics), done here with
-torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+Every pair is independent, so the path shards with NO collective on the data path: the sequence
+sets are replicated on every GPU (C3: 32 MB), the ordered pair matrix is cut into rectangular
+tiles, tiles are dealt to GPUs longest-processing-time-first by DP cells, each GPU aligns its
+tiles and its D2H copies land in its slice of the result ON THE HOST.
+
+* One process driving all GPUs (the product path, taxi2_b200/multi.py): the slices belong to one
+  (page-locked) numpy array.
+* One process per GPU (torchrun): `SharedHostMatrix` is the same thing across processes -- a
+  matrix in host shared memory every rank maps and writes its tiles into.  No NCCL on the data
+  path; the only collective left is `reduce_subset_statistics`, for callers that aggregate per
+  rank instead of over the gathered matrix.
 """
 from __future__ import annotations
 
@@ -58,49 +63,50 @@ def assign_tiles(tiles: list[Tile], world: int) -> list[list[Tile]]:
     return plan
 
 
-def run_sharded(engine_factory, len_x, len_y, tile_x, tile_y, rank: int, world: int, compute_tile) -> dict[int, object]:
-    """Run `compute_tile(tile)` for this rank's share of the tiles; returns {tile index: result}."""
-    tiles = make_tiles(len_x, len_y, tile_x, tile_y)
-    return {tile.index: compute_tile(tile) for tile in assign_tiles(tiles, world)[rank]}
+class SharedHostMatrix:
+    """Host gather across PROCESSES without a collective: a (nx, ny, *item) matrix in shared
+    memory (a file under /dev/shm by default) that every rank of a one-node job maps.  Rank 0
+    creates it, the others open it once it exists; a rank writes exactly the tiles the static plan
+    gives it, so no two ranks touch the same bytes and no locking is needed.  The caller
+    synchronises (a barrier) before reading the whole matrix."""
 
+    def __init__(self, path, shape: tuple, dtype, create: bool):
+        from pathlib import Path
 
-def gather_matrix(local: dict[int, np.ndarray], tiles: list[Tile], shape: tuple, dtype, group=None) -> np.ndarray | None:
-    """Gather per-tile result blocks to rank 0 in reference (row-major) order.
+        self.path = Path(path)
+        self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        if create:
+            self.path.parent.mkdir(parents=True, exist_ok=True)
+            self.array = np.lib.format.open_memmap(self.path, mode="w+", dtype=self.dtype, shape=self.shape)
+        else:
+            self.array = np.load(self.path, mmap_mode="r+")
+            if self.array.shape != self.shape or self.array.dtype != self.dtype:
+                raise ValueError(f"{self.path}: expected {self.shape} {self.dtype}, found {self.array.shape} {self.array.dtype}")
 
-    local[tile.index] has shape (nx, ny, *shape).  Returns the full (NX, NY, *shape) array on rank 0,
-    None elsewhere.  Uses gather_object-free tensor collectives so it works on NCCL and gloo alike.
-    """
-    import torch
-    import torch.distributed as dist
+    def tile(self, tile: Tile) -> np.ndarray:
+        """The slice a tile's results go to (contiguous when the tile spans all columns)."""
+        return self.array[tile.x0:tile.x0 + tile.nx, tile.y0:tile.y0 + tile.ny]
 
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    nx_total = max(t.x0 + t.nx for t in tiles)
-    ny_total = max(t.y0 + t.ny for t in tiles)
-    plan = assign_tiles(tiles, world)
-    out = np.zeros((nx_total, ny_total, *shape), dtype=dtype) if rank == 0 else None
-    backend = dist.get_backend(group) if dist.is_initialized() else "gloo"
-    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    for owner in range(world):
-        for tile in plan[owner]:
-            block_shape = (tile.nx, tile.ny, *shape)
-            if owner == 0:
-                if rank == 0:
-                    out[tile.x0:tile.x0 + tile.nx, tile.y0:tile.y0 + tile.ny] = local[tile.index]
-                continue
-            if rank == owner:
-                dist.send(torch.from_numpy(np.ascontiguousarray(local[tile.index])).to(device), dst=0, group=group)
-            elif rank == 0:
-                buf = torch.empty(block_shape, dtype=torch.from_numpy(np.zeros(1, dtype=dtype)).dtype, device=device)
-                dist.recv(buf, src=owner, group=group)
-                out[tile.x0:tile.x0 + tile.nx, tile.y0:tile.y0 + tile.ny] = buf.cpu().numpy()
-    return out
+    def flush(self) -> None:
+        self.array.flush()
+
+    def unlink(self) -> None:
+        self.array = None
+        self.path.unlink(missing_ok=True)
 
 
 def reduce_subset_statistics(sums: np.ndarray, mins: np.ndarray, maxs: np.ndarray, counts: np.ndarray, group=None):
-    """All-reduce of the per-(metric, subset_x, subset_y) aggregates of
-    /root/reference/src/itaxotools/taxi2/tasks/versus_all.py:57-95 (sum, min, max, n).
-    This is the only collective the path needs (NCCL over NVLink on GPUs)."""
+    """All-reduce of per-(metric, subset_x, subset_y) aggregates of
+    /root/reference/src/itaxotools/taxi2/tasks/versus_all.py:57-95 (sum, min, max, n) for callers
+    that aggregate per rank (NCCL over NVLink on GPUs, gloo on CPU).
+
+    min, max and n are exact.  `sum` is REASSOCIATED: the reference adds the distances of a subset
+    pair in row-major pair order (versus_all.py:67), a per-rank partial sum followed by a tree
+    reduction adds the same numbers in another order, so the mean can differ from the reference's
+    in the last bits (|delta| <= n * 2^-53 * sum|d|) -- invisible at the "{:.4f}" the files are
+    written with, but not bit-identical.  The product path (tasks on a MultiEngine) does not use
+    this: it runs the row-major aggregator (taxi_aggregate_subsets) over the gathered blocks in
+    reference order and is bit-identical on any number of GPUs."""
     import torch
     import torch.distributed as dist
 

@@ -1,5 +1,6 @@
-"""Multi-GPU host logic on CPU: deterministic static tile plan, and the world_size-2 gather /
-statistics reduction over the gloo backend (the N>1 data path has no other collective)."""
+"""Multi-GPU host logic on CPU: deterministic static tile plan, and a world_size-2 job over the
+gloo backend -- every rank writes its tiles into the shared host matrix (the N>1 data path has no
+collective), then the one remaining collective, the subset-statistics reduction."""
 from __future__ import annotations
 
 import os
@@ -11,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from taxi2_b200.sharding import assign_tiles, gather_matrix, make_tiles, reduce_subset_statistics
+from taxi2_b200.sharding import SharedHostMatrix, assign_tiles, make_tiles, reduce_subset_statistics
 
 
 def test_tiles_cover_the_matrix_once():
@@ -53,11 +54,20 @@ def _worker(rank: int, world: int, port: int, out_path: str):
         tiles = make_tiles(lx, ly, 4, 6)
         mine = assign_tiles(tiles, world)[rank]
         # stand-in for the per-tile device result: a function of the global pair index
+        shared_path = out_path + ".matrix.npy"
+        if rank == 0:
+            shared = SharedHostMatrix(shared_path, (19, 23, 2), np.int64, create=True)
+        dist.barrier()
+        if rank != 0:
+            shared = SharedHostMatrix(shared_path, (19, 23, 2), np.int64, create=False)
         local = {}
         for t in mine:
             ii, jj = np.meshgrid(np.arange(t.x0, t.x0 + t.nx), np.arange(t.y0, t.y0 + t.ny), indexing="ij")
             local[t.index] = np.stack([ii * 1000 + jj, lx[ii] * ly[jj]], axis=-1).astype(np.int64)
-        full = gather_matrix(local, tiles, (2,), np.int64)
+            shared.tile(t)[...] = local[t.index]          # the host gather: each rank writes its own tiles
+        shared.flush()
+        dist.barrier()
+        full = np.array(shared.array) if rank == 0 else None
         # per-subset aggregates: each rank contributes its own pairs
         vals = np.concatenate([local[t.index][..., 1].ravel() for t in mine]).astype(np.float64)
         s, mn, mx, n = reduce_subset_statistics(np.array([vals.sum()]), np.array([vals.min()]), np.array([vals.max()]),
