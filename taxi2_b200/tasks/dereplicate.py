@@ -56,7 +56,7 @@ def output_handler(fmt: FileFormat, path: Path):
 
 
 class Dereplicate:
-    rows_per_block = 64
+    rows_per_block = None   # rows per device block (None: about 2M pairs per block)
 
     def __init__(self):
         self.work_dir: Path = None
@@ -96,6 +96,170 @@ class Dereplicate:
         self.paths.distances_matricial = w / "distances" / f"{metric}.matricial.tsv"
 
     def start(self) -> Results:
+        """Block replay of the greedy walk (dereplicate.py:306-351).
+
+        The device is a distance oracle for (block of rows) x (every sequence still alive when the
+        block was scheduled) -- a superset of what the reference would align -- and the walk is
+        replayed on the host row by row with numpy over the columns alive AT THAT MOMENT:
+
+          a row visits its live columns in order (x.id != y.id, neither excluded); every similar
+          y that is not longer than x is excluded; the first similar y that IS longer excludes x,
+          after which the reference's pair filter drops the rest of the row.
+
+        Python objects are only built for pairs that are written (aligned pairs / distance files
+        enabled) and for the summary lines.  When more than half of the loaded sequences have been
+        excluded the survivors are re-loaded, so the device stops computing dead columns.  With
+        several GPUs (task.devices) row blocks are computed ahead on all of them; the walk stays
+        sequential.  Inputs with repeated ids keep the per-pair path (the exclusion set is keyed by
+        id, and the reference's groupby merges neighbouring rows of equal id)."""
+        ids = [s.id for s in self.input]
+        if len(set(ids)) != len(ids):
+            return self._start_per_pair()
+        from ..engine import Engine, scores_vector
+
+        ts = perf_counter()
+        self.excluded = set()
+        self.check_params()
+        self.generate_paths()
+        p = self.params
+        metric = p.distances.metric
+        (col,) = metric_columns([metric])
+        fmt, missing = p.format.float, p.format.missing
+        scale = 100.0 if p.format.percentage_multiply else 1.0
+        similarity = p.thresholds.similarity
+
+        data = [s for s in self.input if len(s.seq) >= p.thresholds.length]   # raw strings, gaps included
+        work = [s.normalize() for s in data] if p.pairs.align else data
+        n = len(data)
+        raw_len = np.array([len(s.seq) for s in data], dtype=np.int64)
+        multi = task_engine(self)
+        scores = scores_vector(dict(p.pairs.scores)) if p.pairs.scores is not None else None
+        if p.pairs.align:
+            multi.set_scores(scores)
+
+        writers = []
+        pairs_file = linear_file = matrix_file = None
+        if p.pairs.align and p.pairs.write:
+            create_parents(self.paths.aligned_pairs)
+            pairs_file = SequencePairHandler.Formatted(self.paths.aligned_pairs, "w")
+            writers.append(pairs_file)
+        if p.distances.write_linear:
+            create_parents(self.paths.distances_linear)
+            linear_file = DistanceHandler.Linear.WithExtras(self.paths.distances_linear, "w", missing=missing, formatter=fmt)
+            writers.append(linear_file)
+        if p.distances.write_matricial:
+            create_parents(self.paths.distances_matricial)
+            matrix_file = DistanceHandler.Matrix(self.paths.distances_matricial, "w", missing=missing, formatter=fmt)
+            writers.append(matrix_file)
+        summary = FileHandler.Tabfile(self.paths.summary, "w", columns=SummaryLine._fields)
+        writers.append(summary)
+        writes_pairs = pairs_file is not None or linear_file is not None or matrix_file is not None
+        side = None   # a context of its own for the consumer's thread (gapped strings of the visited pairs)
+        text = lambda d: missing if d is None else fmt.format(d)  # noqa: E731
+
+        alive = np.ones(n, dtype=bool)
+        total = n * n
+        done, last = 0, perf_counter()
+        self.stats = dict(pairs_computed=0, pairs_visited=0, reloads=0)
+        pointer = 0
+        try:
+            while pointer < n:
+                loaded = np.nonzero(alive)[0]                      # original indices on the device this epoch
+                first_pos = int(np.searchsorted(loaded, pointer))
+                if first_pos >= len(loaded):
+                    break
+                multi.load([work[k].seq for k in loaded], 0)
+                self.stats["reloads"] += 1
+                if pairs_file is not None:
+                    if side is None:
+                        side = Engine(multi.devices[0], scores)
+                    side.load([work[k].seq for k in loaded], 0)
+                m = len(loaded)
+                len_loaded = raw_len[loaded]
+                rows_per_tile = self.rows_per_block or max(1, min(256, (1 << 21) // max(m, 1)))
+                tiles = multi.row_tiles(rows_per_tile, 1, (first_pos, m))
+
+                def compute(eng, tile, slot):
+                    call = eng.align_rect if p.pairs.align else eng.count_rect
+                    return call(tile.x0, tile.nx, 0, m, want=("metrics",))["metrics"][..., col]
+
+                blocks = multi.run_tiles(tiles, compute, depth=2, ordered=True)
+                try:
+                    for tile, values in blocks:
+                        self.stats["pairs_computed"] += tile.nx * m
+                        for bx in range(tile.nx):
+                            pos = tile.x0 + bx
+                            i = int(loaded[pos])
+                            pointer = i + 1
+                            if not alive[i]:
+                                continue
+                            live = alive[loaded]
+                            live[pos] = False                      # x.id != y.id
+                            idx = np.nonzero(live)[0]
+                            if idx.size == 0:
+                                continue
+                            d = values[bx, idx] * scale
+                            with np.errstate(invalid="ignore"):
+                                similar = np.isfinite(d) & (d <= similarity)
+                            longer = similar & (len_loaded[idx] > raw_len[i])
+                            stop = int(np.argmax(longer)) if longer.any() else idx.size - 1
+                            visited = idx[: stop + 1]
+                            dv, sv = d[: stop + 1], similar[: stop + 1]
+                            x = data[i]
+                            first_d = float(dv[0]) if np.isfinite(dv[0]) else None
+                            if writes_pairs:
+                                strings = None
+                                if pairs_file is not None:   # one launch for the row's visited columns
+                                    ax, ay, _ = side.align_strings(np.full(len(visited), pos, dtype=np.int32), visited.astype(np.int32))
+                                    strings = (ax, ay)
+                                for q, vpos in enumerate(visited):
+                                    j = int(loaded[vpos])
+                                    if strings is not None:
+                                        pair = SequencePair(Sequence(x.id, strings[0][q].decode("latin-1"), work[i].extras),
+                                                            Sequence(data[j].id, strings[1][q].decode("latin-1"), work[j].extras))
+                                        pairs_file.write(pair)
+                                    else:
+                                        pair = SequencePair(work[i], work[j])
+                                    distance = Distance(metric, pair.x, pair.y, float(dv[q]) if np.isfinite(dv[q]) else None)
+                                    if linear_file:
+                                        linear_file.write(distance)
+                                    if matrix_file:
+                                        matrix_file.write(distance)
+                            for q in np.nonzero(sv)[0]:
+                                j = int(loaded[visited[q]])
+                                y_info = (data[j].id, int(raw_len[j]), float(dv[q]))
+                                x_info = (x.id, int(raw_len[i]), first_d)
+                                inc, exc = (y_info, x_info) if longer[q] else (x_info, y_info)
+                                gone = i if longer[q] else j
+                                alive[gone] = False
+                                self.excluded.add(data[gone].id)
+                                summary.write((x.id, str(int(raw_len[i])), inc[0], str(inc[1]), text(inc[2]), exc[0], str(exc[1]), text(exc[2])))
+                            done += len(visited)
+                            self.stats["pairs_visited"] += len(visited)
+                            now = perf_counter()
+                            if now - last >= self.progress_interval:
+                                self.progress_handler("distance.x.id", done, total - len(self.excluded) * n)
+                                last = now
+                        # the device keeps computing the columns that died since the load: start over
+                        # with the survivors once that is more than half of the loaded set
+                        if int(alive[loaded].sum()) * 2 < m and pointer < n:
+                            break
+                finally:
+                    blocks.close()
+            self.progress_handler("Finalizing...", total, total)
+        finally:
+            for w in writers:
+                w.close()
+            if side is not None:
+                side.close()
+
+        with output_handler(self.output_format, self.paths.dereplicated) as kept, \
+                output_handler(self.output_format, self.paths.excluded) as dropped:
+            for sequence in data:
+                (dropped if sequence.id in self.excluded else kept).write(sequence)
+        return Results(self.work_dir, perf_counter() - ts)
+
+    def _start_per_pair(self) -> Results:
         from ..engine import scores_vector
 
         ts = perf_counter()
@@ -140,8 +304,9 @@ class Dereplicate:
         def infos():
             """The reference's stream of visited pairs, in order, with the exclusion set consulted
             at the moment each pair would have been pulled."""
-            for x0 in range(0, n, self.rows_per_block):
-                rows = [i for i in range(x0, min(n, x0 + self.rows_per_block)) if data[i].id not in self.excluded]
+            per = self.rows_per_block or 64
+            for x0 in range(0, n, per):
+                rows = [i for i in range(x0, min(n, x0 + per)) if data[i].id not in self.excluded]
                 cols = [j for j in range(n) if data[j].id not in self.excluded]
                 if not rows or not cols:
                     continue

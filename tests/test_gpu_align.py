@@ -232,6 +232,39 @@ def test_strings_and_metrics_from_one_launch(engine):
         assert tuple(res["counts"][k]) == tuple(c)
 
 
+@pytest.mark.parametrize("scores", [(1, -1, -8, -1, -1, -1), (1, 0, 0, 0, 0, 0), (2, -3, -5, -2, -4, -1), (1, -1, -1, -1, -2, -2),
+                                    (10, 0, -10, -6, 0, 0), (2, -1, -3, -2, -1, -1), (3, -4, -90, -1, -1, -1)])
+def test_emitted_alignments_rescore_to_the_optimum(engine, scores):
+    """Independent of the oracle: every gapped pair the CUDA path emits (all three kernel variants),
+    re-scored column by column under the six scores with end / internal gap typing, reproduces the
+    score the kernel reported, and that score is the optimum of a separate score-only dynamic
+    programme (tests/rescore.py).  Pins optimality; only the choice among co-optimal alignments
+    rests on the oracle."""
+    from rescore import best_score, rescore
+
+    rng = np.random.default_rng(abs(hash(scores)) % (2**32))
+    xs, ys = random_pairs(rng, 120, 1, 50, sub=0.3, indel=0.1, alphabet=b"ACGTN")
+    xs2, ys2 = random_pairs(rng, 80, 1, 50, sub=0.3, indel=0.1, alphabet=b"AT")
+    xs, ys = xs + xs2, ys + ys2
+    best = [best_score(x.decode(), y.decode(), scores) for x, y in zip(xs, ys)]
+    px = np.arange(len(xs), dtype=np.int32)
+    for force_general, force_top in ((0, 0), (0, 1), (1, 0)):
+        engine.set_option("force_general", force_general)
+        engine.set_option("force_top", force_top)
+        try:
+            engine.set_scores(scores)
+            engine.load(xs, 0)
+            engine.load(ys, 1)
+            ax, ay, sc = engine.align_strings(px, px)
+        finally:
+            engine.set_option("force_general", 0)
+            engine.set_option("force_top", 0)
+        for k in range(len(xs)):
+            gx, gy = ax[k].decode(), ay[k].decode()
+            assert gx.replace("-", "") == xs[k].decode() and gy.replace("-", "") == ys[k].decode()
+            assert rescore(gx, gy, scores) == sc[k] == best[k], (force_general, force_top, xs[k], ys[k])
+
+
 def test_extra_symbols(engine):
     """IUPAC symbols: up to seven distinct symbols stay on the fast path, more fall back."""
     rng = np.random.default_rng(5)
