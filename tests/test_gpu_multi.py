@@ -109,7 +109,7 @@ def test_best_rows_with_undefined_rows(single):
     single.load(["ACGTACGT", "NNNNNNNN", "ACGAACGT"], 0)
     single.load(["NNNNNNNN", "ACGTACGA", "ACGTACGT", "ACGTACGT"], 1)
     got = single.best_rows(0, 3, 0, 4, 0, align=False)
-    assert list(got["index"]) == [2, -1, 1]
+    assert list(got["index"]) == [2, -1, 2]     # one mismatch against reference 2, two against reference 1
     assert np.isnan(got["metrics"][1]).all() and got["metrics"][0, 0] == 0.0
     assert not got["counts"][1].any()
 

@@ -31,11 +31,16 @@ def rect(n, length, **options):
 rect(384, 650)
 rect(256, 1200)
 rect(256, 650, force_general=1)
-rng = np.random.default_rng(9)
-al = np.frombuffer(b"ACGT-N", dtype=np.uint8)
-eng.load([al[rng.choice(6, 618, p=[.24, .24, .24, .24, .03, .01])].tobytes() for _ in range(4096)], 0)
-c = torch.empty((4096 * 4096, 4), dtype=torch.int32, device="cuda")
-m = torch.empty((4096 * 4096, 4), dtype=torch.float64, device="cuda")
-eng.count_rect_device(0, 4096, 0, 4096, c.data_ptr(), m.data_ptr())
-eng.sync()
-print("count_rect ms", round(eng.stats()["kernel_ms"], 2))
+# alignment-free rectangle at BASELINE C2 size: 9000 pre-aligned rows x 618 columns, one launch
+sys.path.insert(0, str(ROOT))
+from bench import make_prealigned  # noqa: E402
+
+data, off = make_prealigned(9000)
+n = len(off) - 1
+eng.load((data, off), 0)
+c = torch.empty((n * n, 4), dtype=torch.int32, device="cuda")
+m = torch.empty((n * n, 4), dtype=torch.float64, device="cuda")
+for _ in range(2):
+    eng.count_rect_device(0, n, 0, n, c.data_ptr(), m.data_ptr())
+    eng.sync()
+    print("count_rect", n, "x", n, "ms", round(eng.stats()["kernel_ms"], 3))
