@@ -24,21 +24,36 @@ struct ScoreSet {
 
 // constants of the packed 16-bit fast path (gotoh_pair16.cuh), transformed score space, x16
 struct Fast16 {
-    int32_t D16;                       // (match - mismatch) * 16 <= 127: penalty of a mismatching column (a match costs 0)
-    uint32_t tlo, thi;                 // PRMT table indexed by the XOR of two symbol codes: byte 0 = 0, bytes 1..7 = D16
+    int32_t D16;                       // (match - mismatch) * 16: penalty of a mismatching column (a match costs 0)
+    uint32_t negD;                     // 2^32 - D16: (1 per differing half) * negD + H is H - D16 in those halves, one IMAD
     int32_t PoX, PeX, PeoX, PeeX;      // vertical   (Ix) penalties 16*(match - g): internal open/extend, end open/extend
     int32_t PoY, PeY, PeoY, PeeY;      // horizontal (Iy) penalties -16*g
     int32_t beta;                      // row potential of the transformed space (= match), unscaled
     int32_t neg;                       // "minus infinity" of the dead slots (multiple of 16, above every penalty)
     int32_t bias;                      // value representing transformed score 0 (multiple of 16), placed by the host so that
                                        // every reachable value of the padded DP fits the unsigned 16-bit window
-    uint32_t class_lut;                // nibble k = base_class of the symbol with code k (traceback counts work on codes)
-    uint32_t ascii_lo, ascii_hi;       // byte k = the symbol with code k (gapped strings are written from codes)
+    uint32_t class_lut[2];             // nibble k = base_class of the symbol with code k (traceback counts work on codes)
+    uint32_t ascii[4];                 // byte k = the symbol with code k (gapped strings are written from codes)
     int32_t has_gap_symbol;            // '-' occurs inside the loaded sequences (input that was not normalized)
     int32_t dead_extra;                // largest difference of the x lengths of the two pairs of a unit that `neg` is budgeted for
 };
 
-// Symbol codes are stored per sequence with CODE_LEAD pad codes (7 = "matches nothing") in front
+// Symbol codes are 0..14 (the fifteen IUPAC nucleotide symbols fit; more distinct symbols send the
+// job to the general kernel), 15 = pad.
+constexpr int CODE_SYMBOLS = 15;
+constexpr uint32_t CODE_PADSYM = 15u;
+
+__device__ __forceinline__ int code_class(const Fast16& f, int code)      // base_class of a symbol code
+{
+    return (int)((f.class_lut[code >> 3] >> (4 * (code & 7))) & 7u);
+}
+
+__device__ __forceinline__ uint8_t code_ascii(const Fast16& f, int code)  // the symbol itself
+{
+    return (uint8_t)(f.ascii[code >> 2] >> (8 * (code & 3)));
+}
+
+// Symbol codes are stored per sequence with CODE_LEAD pad codes (15 = "matches no symbol") in front
 // and one behind, so the DP's one-step-ahead fetch of the next column symbol needs no lower bound
 // check at all (the wavefront skew is at most 31 columns) and only a clamp at the upper end.
 constexpr int CODE_LEAD = 32;
@@ -106,21 +121,87 @@ __host__ __device__ __forceinline__ int base_class(int c)
     return k;
 }
 
+// ---- lean fp64 arithmetic for the metric epilogue ----------------------------------------------
+// The metrics cost more instructions than the counting itself when written with the compiler's
+// generic `/`, log() and sqrt() (special-case paths, 64-bit immediates materialised per use).  The
+// operands here are tame -- ratios of small non-negative integers, logarithm arguments in (0, 1] --
+// so the epilogue uses straight-line versions: a Newton reciprocal from MUFU.RCP64H shared by all
+// divisions with the same divisor, each quotient finished with the remainder correction
+// (q + (a - b*q) * r), which makes it the correctly rounded IEEE quotient (so p, p-gaps and every
+// intermediate ratio are bit-identical to `a / b`), and the fdlibm log kernel on the reduced
+// mantissa.  tools/metrics_emul.c replays the same operation sequence on the CPU against libm:
+// p / p-gaps bit-exact, jc / k2p within 3e-16 relative over 15 M count tuples.
+__constant__ double kLogCoef[9] = {
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+    6.93147180369123816490e-01 /* ln2_hi */, 1.90821492927058770002e-10 /* ln2_lo */};
+
+__device__ __forceinline__ double rcp_full(double b)   // 1 / b to full precision (b > 0, normal)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
+}
+
+__device__ __forceinline__ double div_by(double a, double b, double r)   // a / b correctly rounded, r = rcp_full(b)
+{
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+__device__ __forceinline__ double sqrt_pos(double a)   // sqrt(a), a > 0 normal
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double h = 0.5 * y, g = a * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    return fma(fma(-g, g, a), h, g);
+}
+
+__device__ __forceinline__ double log_pos(double x)   // log(x), x > 0 normal (fdlibm e_log.c kernel)
+{
+    int hx = __double2hiint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;            // mantissa above sqrt(2): use half of it
+    k += i >> 20;
+    const double f = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x)) - 1.0;
+    const double t = 2.0 + f;
+    const double s = div_by(f, t, rcp_full(t));
+    const double dk = (double)k;
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return fma(dk, kLogCoef[7], -((hfsq - fma(s, hfsq + R, dk * kLogCoef[8])) - f));
+}
+
 // distances.py:319-348 formulas in fp64; NaN where the reference yields None.
 __device__ __forceinline__ void metrics_from_counts(int same, int ts, int tv, int gap, double out[4])
 {
-    const double n = (double)same + (double)ts + (double)tv;
+    const double n = (double)(same + ts + tv);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     if (!(n > 0.0)) { out[0] = out[1] = out[2] = out[3] = nan; return; }
-    const double d = (double)ts + (double)tv;
-    const double p = d / n;
+    const double d = (double)(ts + tv), g = (double)gap;
+    const double rn = rcp_full(n);
+    const double p = div_by(d, n, rn);
     out[0] = p;
-    out[1] = (d + (double)gap) / (n + (double)gap);
-    const double P = (double)ts / n, Q = (double)tv / n;
-    const double jc = -0.75 * log(1.0 - 4.0 * p / 3.0);
-    const double k2 = -0.5 * log((1.0 - 2.0 * P - Q) * sqrt(1.0 - 2.0 * Q));
-    out[2] = isfinite(jc) ? jc + 0.0 : nan;
-    out[3] = isfinite(k2) ? k2 + 0.0 : nan;
+    out[1] = div_by(d + g, n + g, rcp_full(n + g));
+    const double P = div_by((double)ts, n, rn), Q = div_by((double)tv, n, rn);
+    const double u = 1.0 - div_by(4.0 * p, 3.0, 1.0 / 3.0);           // jc = -3/4 ln(1 - 4p/3)
+    const double b = 1.0 - 2.0 * Q, a = 1.0 - 2.0 * P - Q;             // k2p = -1/2 ln((1 - 2P - Q) sqrt(1 - 2Q))
+    const double v = (a > 0.0 && b > 0.0) ? a * sqrt_pos(b) : -1.0;
+    // a non-positive argument is -inf / NaN in the reference (None); "+ 0.0" folds -0.0 into +0.0
+    out[2] = u > 0.0 ? -0.75 * log_pos(u) + 0.0 : nan;
+    out[3] = v > 0.0 ? -0.5 * log_pos(v) + 0.0 : nan;
 }
 
 }  // namespace taxi

@@ -53,12 +53,17 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint3
     return r;
 }
 
-__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel)
+// Diagonal candidate of a cell: H(i-1, j-1) minus the mismatch penalty, for both pairs at once.
+// a2 / b2 hold the row / column symbol code of pair A in the low half and of pair B in the high
+// half; min(a ^ b, 1) is 1 per half where they differ (VIMNMX.U16x2, full rate on either pipe),
+// and one IMAD folds the multiplication by the penalty into the subtraction -- it runs on the fma
+// pipe, off the alu pipe that bounds this kernel, and off the row-to-row dependency chain.
+// Works for any number of symbol codes and any penalty (the earlier LOP3 + PRMT table lookup
+// needed codes below 8 and a one-byte penalty).
+__device__ __forceinline__ uint32_t diag_candidate(uint32_t Hd, uint32_t a2, uint32_t b2, uint32_t negD)
 {
-    // PRMT without the "selector & 0x7777" that __byte_perm adds (our selector nibbles are 0..7)
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
+    const uint32_t ne = __vminu2(a2 ^ b2, 0x00010001u);
+    return ne * negD + Hd;
 }
 
 template <int H> struct Pair16Geom {
@@ -137,9 +142,9 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
     const bool mine = lane < V;
     const unsigned visited = 0xffffffffu >> (32 - V);
-    const uint32_t lut = a.f16.class_lut;
+    const Fast16& f = a.f16;
     if (state == 0) {
-        const int ka = (int)((lut >> (4 * w.ca)) & 7u), kb = (int)((lut >> (4 * w.cb)) & 7u);
+        const int ka = code_class(f, w.ca), kb = code_class(f, w.cb);
         const bool both = (ka | kb) < 4;
         const int d = ka ^ kb;
         w.n += (mine && both);
@@ -164,12 +169,12 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
         }
     } else {
         // a gap run: every column whose symbol is a base is a gap column, pending until the next both-real column
-        const int k = (int)((lut >> (4 * (state == 1 ? w.ca : w.cb))) & 7u);
+        const int k = code_class(f, state == 1 ? w.ca : w.cb);
         w.pend += __popc(__ballot_sync(TAXI_FULL_MASK, k < 4) & visited);
     }
     if (a.aln_x != nullptr && mine) {
-        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, w.ca);
-        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, w.cb);
+        a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : code_ascii(f, w.ca);
+        a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : code_ascii(f, w.cb);
     }
     w.wpos -= V;
     w.i -= V * di; w.j -= V * dj;
@@ -181,13 +186,13 @@ __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lan
     if (a.aln_x != nullptr) {
         // leading end gap: whatever is left of x (vertical) or y (horizontal)
         for (int k = lane; k < w.i; k += 32) {
-            a.aln_x[w.wpos - 1 - k] = (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, (int)__ldg(w.x + w.i - 1 - k));
+            a.aln_x[w.wpos - 1 - k] = code_ascii(a.f16, (int)__ldg(w.x + w.i - 1 - k));
             a.aln_y[w.wpos - 1 - k] = '-';
         }
         w.wpos -= w.i;
         for (int k = lane; k < w.j; k += 32) {
             a.aln_x[w.wpos - 1 - k] = '-';
-            a.aln_y[w.wpos - 1 - k] = (uint8_t)__byte_perm(a.f16.ascii_lo, a.f16.ascii_hi, (int)__ldg(w.y + w.j - 1 - k));
+            a.aln_y[w.wpos - 1 - k] = code_ascii(a.f16, (int)__ldg(w.y + w.j - 1 - k));
         }
         w.wpos -= w.j;
         if (lane == 0) a.aln_start[w.p] = w.wpos;
@@ -271,9 +276,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
 #pragma unroll
     for (int r = 0; r < H; ++r) {
         const int i = itop + r;
-        const uint32_t c0 = (i <= A.nA) ? (uint32_t)__ldg(A.xc + min(i, A.nA) - 1) : 7u;
-        const uint32_t c1 = (i <= B.nA) ? (uint32_t)__ldg(B.xc + min(i, B.nA) - 1) : 7u;
-        a2[r] = c0 | (c1 << 8);
+        const uint32_t c0 = (i <= A.nA) ? (uint32_t)__ldg(A.xc + min(i, A.nA) - 1) : CODE_PADSYM;
+        const uint32_t c1 = (i <= B.nA) ? (uint32_t)__ldg(B.xc + min(i, B.nA) - 1) : CODE_PADSYM;
+        a2[r] = c0 | (c1 << 16);
         const uint32_t xb = (uint32_t)f.bias - f.PeoX - (uint32_t)(i - 1) * f.PeeX + 2u;   // Ix(i,0), tagged as state Ix
         Hl[r] = pack16(xb, xb);
         Yn[r] = pack16((uint32_t)f.neg, (uint32_t)f.neg);                                        // no Ix->Iy: Iy(i,1) opens from M only
@@ -313,9 +318,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
                 rX = pack16((uint32_t)f.neg, (uint32_t)f.neg);
             }
             if (active) {
-                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : 7u;
-                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : 7u;
-                const uint32_t b2 = b0 | (b1 << 8);
+                const uint32_t b0 = (j <= A.nB) ? (uint32_t)__ldg(A.yc + j - 1) : CODE_PADSYM;
+                const uint32_t b1 = (j <= B.nB) ? (uint32_t)__ldg(B.yc + j - 1) : CODE_PADSYM;
+                const uint32_t b2 = b0 | (b1 << 16);
                 const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
                 const int xe0 = (j == A.nB) ? f.PeeX : f.PeX, xe1 = (j == B.nB) ? f.PeeX : f.PeX;
                 const uint32_t ncXM = pack16((uint32_t)(1 - xo0), (uint32_t)(1 - xo1));  // M(tag 3) -> Ix candidate with bit 2 set
@@ -325,9 +330,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
                 uint32_t tprev = 0;
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
-                    const uint32_t sel = lop3_xor_or(a2[r], b2, 0x8080u);
-                    const uint32_t sub = prmt_raw(f.tlo, f.thi, sel);   // mismatch penalty (0 or D16) per half
-                    const uint32_t Mr = Hd - sub;
+                    const uint32_t Mr = diag_candidate(Hd, a2[r], b2, f.negD);
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);                   // 4-bit trace code per half (+ score bits above)
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
@@ -384,7 +387,6 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     constexpr int HB = Pair16Geom<H>::HB;
     constexpr int WORDS = Pair16Geom<H>::WORDS;
     constexpr int SL = 32 * H;
-    constexpr uint32_t PAD = 7u;                         // symbol past the end of y: matches nothing
     const Fast16& f = a.f16;
     const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
     const int offA = SL - A.nA, offB = SL - B.nA;        // slot of row 1; row 0 sits in slot off-1
@@ -404,9 +406,9 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
     for (int r = 0; r < H; ++r) {
         const int s = lane * H + r;
         const int iA = s - offA + 1, iB = s - offB + 1;
-        const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
-        const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
-        a2[r] = c0 | (c1 << 8);
+        const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : CODE_PADSYM;
+        const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : CODE_PADSYM;
+        a2[r] = c0 | (c1 << 16);
         Hl[r] = pack16(col0_H(iA), col0_H(iB));
         // Iy(i, 1): only row 0 has one (the leading end gap, opened from M(0,0)); no Ix->Iy elsewhere
         const uint32_t y0 = (uint32_t)f.bias - f.PeoY + 8u;
@@ -449,8 +451,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
             const uint32_t b0 = nb0, b1 = nb1;
             fetch_b(j + 1, nb0, nb1);
             if (active) {
-                const uint32_t b2 = b0 | (b1 << 8);
-                auto sub_of = [&](int r) -> uint32_t { return prmt_raw(f.tlo, f.thi, lop3_xor_or(a2[r], b2, 0x8080u)); };   // mismatch penalty per half
+                const uint32_t b2 = b0 | (b1 << 16);
                 uint32_t ncXM = ncXMi, cXX = cXXi;
                 if (j == A.nB || j == B.nB) {   // a vertical gap in a pair's last column is an end gap
                     const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
@@ -461,11 +462,11 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 uint32_t Xin = rX;
                 uint32_t tw[WORDS];
                 uint32_t tprev = 0;
-                uint32_t Mr = Hd_saved - sub_of(0);
+                uint32_t Mr = diag_candidate(Hd_saved, a2[0], b2, f.negD);
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     uint32_t Mr_next = 0;
-                    if (r + 1 < H) Mr_next = Hl[r] - sub_of(r + 1);   // needs H(i, j-1) before it is overwritten
+                    if (r + 1 < H) Mr_next = diag_candidate(Hl[r], a2[r + 1], b2, f.negD);   // needs H(i, j-1) before it is overwritten
                     const uint32_t Yin = Yn[r];
                     const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
@@ -515,7 +516,6 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
     constexpr int HB = Pair16Geom<H>::HB;
     constexpr int WORDS = Pair16Geom<H>::WORDS;
     constexpr int SL = 32 * H;
-    constexpr uint32_t PAD = 7u;
     const Fast16& f = a.f16;
     const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
     const int nstripes = (max(A.nA, B.nA) + 1 + SL - 1) / SL;   // rows 0..nA of the longer pair
@@ -546,9 +546,9 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
         for (int r = 0; r < H; ++r) {
             const int s = st * SL + lane * H + r;
             const int iA = s - offA + 1, iB = s - offB + 1;
-            const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : 7u;
-            const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : 7u;
-            a2[r] = c0 | (c1 << 8);
+            const uint32_t c0 = (iA >= 1) ? (uint32_t)__ldg(A.xc + max(iA, 1) - 1) : CODE_PADSYM;
+            const uint32_t c1 = (iB >= 1) ? (uint32_t)__ldg(B.xc + max(iB, 1) - 1) : CODE_PADSYM;
+            a2[r] = c0 | (c1 << 16);
             Hl[r] = pack16(col0_H(iA), col0_H(iB));
             const uint32_t y0 = (uint32_t)f.bias - f.PeoY + 8u;
             Yn[r] = pack16(iA == 0 ? y0 : (uint32_t)f.neg, iB == 0 ? y0 : (uint32_t)f.neg);
@@ -565,7 +565,7 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
         // the y symbols of a column and, for the top slot of a later stripe, the values the previous
         // stripe left in the boundary buffer are fetched one step ahead, so that their latency hides
         // behind a whole step (the pad codes around every sequence make the symbol fetch a clamp)
-        uint32_t nb0 = PAD, nb1 = PAD, nbX = NEG2, nbH = NEG2;
+        uint32_t nb0 = CODE_PADSYM, nb1 = CODE_PADSYM, nbX = NEG2, nbH = NEG2;
         auto fetch_next = [&](int jj) {
             nb0 = (uint32_t)__ldg(A.yc + min(jj, A.nB + 1) - 1);
             nb1 = (uint32_t)__ldg(B.yc + min(jj, B.nB + 1) - 1);
@@ -587,8 +587,7 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
                 }
                 fetch_next(j + 1);
                 if (active) {
-                    const uint32_t b2 = b0 | (b1 << 8);
-                    auto sub_of = [&](int r) -> uint32_t { return prmt_raw(f.tlo, f.thi, lop3_xor_or(a2[r], b2, 0x8080u)); };
+                    const uint32_t b2 = b0 | (b1 << 16);
                     uint32_t ncXM = ncXMi, cXX = cXXi;
                     if (j == A.nB || j == B.nB) {
                         const int xo0 = (j == A.nB) ? f.PeoX : f.PoX, xo1 = (j == B.nB) ? f.PeoX : f.PoX;
@@ -599,11 +598,11 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
                     uint32_t Xin = rX;
                     uint32_t tw[WORDS];
                     uint32_t tprev = 0;
-                    uint32_t Mr = Hd_saved - sub_of(0);
+                    uint32_t Mr = diag_candidate(Hd_saved, a2[0], b2, f.negD);
 #pragma unroll
                     for (int r = 0; r < H; ++r) {
                         uint32_t Mr_next = 0;
-                        if (r + 1 < H) Mr_next = Hl[r] - sub_of(r + 1);
+                        if (r + 1 < H) Mr_next = diag_candidate(Hl[r], a2[r + 1], b2, f.negD);
                         const uint32_t Yin = Yn[r];
                         const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                         const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);

@@ -85,7 +85,7 @@ struct taxi_ctx {
     int32_t raw_scores[TAXI_NSCORES]{};
     bool have_scores = false;
     // symbol codebook shared by both sets: A C G T N are fixed, up to two more symbols are
-    // assigned in order of appearance; more than 7 symbols disables the packed fast path
+    // assigned in order of appearance; more than CODE_SYMBOLS (15) symbols disable the packed fast path
     int16_t codebook[256];
     int ncodes = 5;
     bool codebook_ok = true;
@@ -177,7 +177,7 @@ __global__ void encode_codes_kernel(const uint8_t* __restrict__ bytes, const int
         const int len = (int)(off[seq + 1] - o);
         uint8_t* dst = out + code_offset(o, seq) - CODE_LEAD;
         for (int k = threadIdx.x; k < len + CODE_PAD; k += blockDim.x)
-            dst[k] = (k < CODE_LEAD || k == CODE_LEAD + len) ? (uint8_t)7 : lut[bytes[o + k - CODE_LEAD]];
+            dst[k] = (k < CODE_LEAD || k == CODE_LEAD + len) ? (uint8_t)CODE_PADSYM : lut[bytes[o + k - CODE_LEAD]];
     }
 }
 
@@ -211,7 +211,6 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, int dead_ext
     if (io == ie && eo == ee) return false;                 // Needleman-Wunsch order: general kernel
     if (match < mm || match < 0) return false;
     const int beta = match, D = match - mm;
-    if (D * 16 > 127) return false;
     // every gap step must be a non-negative penalty in the transformed space S' = S - match*i
     const int gaps[4] = {io, ie, eo, ee};
     for (int g : gaps) if (g > 0) return false;
@@ -243,14 +242,15 @@ bool fast16_eligible(const taxi_ctx* c, int max_rows, int max_cols, int dead_ext
     }
     Fast16 f;
     f.D16 = 16 * D; f.beta = beta;
-    f.tlo = (uint32_t)f.D16 * 0x01010100u; f.thi = (uint32_t)f.D16 * 0x01010101u;
-    f.class_lut = 0x55555555u; f.ascii_lo = f.ascii_hi = 0; f.has_gap_symbol = 0;
+    if (D > 2000) return false;
+    f.negD = 0u - (uint32_t)f.D16;
+    f.class_lut[0] = f.class_lut[1] = 0x55555555u;   // unused codes and the pad: "missing"
+    f.ascii[0] = f.ascii[1] = f.ascii[2] = f.ascii[3] = 0; f.has_gap_symbol = 0;
     for (int ch = 0; ch < 256; ++ch) {
         const int k = c->codebook[ch];
-        if (k < 0 || k > 6) continue;
-        f.class_lut = (f.class_lut & ~(0xFu << (4 * k))) | ((uint32_t)base_class(ch) << (4 * k));
-        if (k < 4) f.ascii_lo |= (uint32_t)ch << (8 * k);
-        else f.ascii_hi |= (uint32_t)ch << (8 * (k - 4));
+        if (k < 0 || k >= CODE_SYMBOLS) continue;
+        f.class_lut[k >> 3] = (f.class_lut[k >> 3] & ~(0xFu << (4 * (k & 7)))) | ((uint32_t)base_class(ch) << (4 * (k & 7)));
+        f.ascii[k >> 2] |= (uint32_t)ch << (8 * (k & 3));
         if (ch == '-') f.has_gap_symbol = 1;
     }
     f.PoX = 16 * (match - io); f.PeX = 16 * (match - ie); f.PeoX = 16 * (match - eo); f.PeeX = 16 * (match - ee);
@@ -634,13 +634,13 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
     }
     for (int64_t k = 0; k < s.total && c->codebook_ok; ++k) {
         if (c->codebook[bytes[k]] < 0) {
-            if (c->ncodes >= 7) c->codebook_ok = false;
+            if (c->ncodes >= CODE_SYMBOLS) c->codebook_ok = false;
             else c->codebook[bytes[k]] = (int16_t)c->ncodes++;
         }
     }
     if (c->codebook_ok) {
         uint8_t book[256];
-        for (int k = 0; k < 256; ++k) book[k] = (uint8_t)(c->codebook[k] < 0 ? 7 : c->codebook[k]);
+        for (int k = 0; k < 256; ++k) book[k] = (uint8_t)(c->codebook[k] < 0 ? CODE_PADSYM : c->codebook[k]);
         CUDA_TRY(c->d_codebook.reserve(256));
         CUDA_TRY(cudaMemcpyAsync(c->d_codebook.p, book, 256, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // `book` is a stack buffer

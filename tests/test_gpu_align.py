@@ -129,8 +129,10 @@ def test_fast_path_score_sets(engine):
     for scores in [(1, -1, -8, -1, -1, -1), (2, -1, -3, -2, -1, -1), (4, -3, -9, -3, -3, -3), (1, -1, -2, -1, -2, -1), (3, -2, -6, -2, -3, -2), (2, -2, -7, -3, -4, -2)]:
         check_pairs(engine, xs, ys, scores, expect_fast=True)
         check_pairs(engine, xs2, ys2, scores, expect_fast=True)
-    # match - mismatch > 7 does not fit the one-byte penalty table: general kernel
-    check_pairs(engine, xs[:60], ys[:60], (5, -4, -10, -4, -4, -4), expect_fast=False)
+    # match - mismatch > 7 (beyond the one-byte penalty table of round 1): the penalty is applied by an IMAD now
+    check_pairs(engine, xs[:60], ys[:60], (5, -4, -10, -4, -4, -4), expect_fast=True)
+    short = [k for k in range(len(xs2)) if len(xs2[k]) <= 40 and len(ys2[k]) <= 40]
+    check_pairs(engine, [xs2[k] for k in short], [ys2[k] for k in short], (20, -30, -70, -25, -40, -25), expect_fast=True)
 
 
 def test_mixed_lengths_in_one_warp(engine):
@@ -266,11 +268,16 @@ def test_emitted_alignments_rescore_to_the_optimum(engine, scores):
 
 
 def test_extra_symbols(engine):
-    """IUPAC symbols: up to seven distinct symbols stay on the fast path, more fall back."""
+    """IUPAC symbols: up to fifteen distinct symbols (all IUPAC nucleotide codes) stay on the fast
+    path, more fall back to the general kernel."""
     rng = np.random.default_rng(5)
     xs, ys = random_pairs(rng, 60, 20, 150, alphabet=b"ACGTNRY")
     check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
     xs, ys = random_pairs(rng, 60, 20, 150, alphabet=b"ACGTNRYKMSW")
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+    xs, ys = random_pairs(rng, 80, 20, 700, sub=0.1, indel=0.02, alphabet=b"ACGTNRYKMSWBDHV")
+    check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=True)
+    xs, ys = random_pairs(rng, 60, 20, 150, alphabet=b"ACGTNRYKMSWBDHVXZ")
     check_pairs(engine, xs, ys, (1, -1, -8, -1, -1, -1), expect_fast=False)
 
 
