@@ -189,7 +189,7 @@ constexpr int COUNT_TY = 256;
 constexpr int COUNT_RX = 4;
 constexpr int COUNT_SLAB = 64;   // x rows staged in shared memory per block (fewer when the sequences are long)
 
-__global__ void __launch_bounds__(COUNT_TY, 2) count_rect_kernel(const CountArgs a)
+__global__ void __launch_bounds__(COUNT_TY, 3) count_rect_kernel(const CountArgs a)
 {
     extern __shared__ uint4 xs[];   // [slab][W]
     const int W = min(a.x.W, a.y.W);

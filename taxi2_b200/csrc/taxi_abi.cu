@@ -926,10 +926,10 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
         return TAXI_OK;
     }
     const int W = std::min(X.W, Y.W);
-    // x rows per block: as many as fit ~96 KB of shared memory (two blocks per SM), at most COUNT_SLAB
+    // x rows per block: as many as fit ~64 KB of shared memory (three blocks per SM), at most COUNT_SLAB
     const size_t row_bytes = (size_t)W * sizeof(uint4);
     if (row_bytes > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
-    a.slab = (int32_t)std::max<size_t>(1, std::min<size_t>(COUNT_SLAB, (96 * 1024) / row_bytes));
+    a.slab = (int32_t)std::max<size_t>(1, std::min<size_t>(COUNT_SLAB, (64 * 1024) / row_bytes));
     const size_t smem = (size_t)a.slab * row_bytes;
     CUDA_TRY(cudaFuncSetAttribute(count_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // grid.y is limited to 65535 slabs: taller rectangles go in several launches
