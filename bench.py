@@ -567,8 +567,8 @@ def run_config(args) -> None:
         n = len(off) - 1
         multi.load((data, off), 0)
         pairs = n * n
-        # device-resident: the whole matrix per step on GPU 0 (N > 1: row tiles, results left in HBM)
-        tiles = multi.row_tiles()
+        # device-resident: one block of rows per GPU, results left in HBM
+        tiles = multi.row_tiles(rows_per_tile=-(-n // world))
 
         def resident(engine, tile, slot):
             engine.count_rect_resident(tile.x0, tile.nx, 0, n)

@@ -795,6 +795,8 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
 // pairs, so a large rectangle (BASELINE C3 is 2.5e9 ordered pairs = 120 GB of results) is walked
 // in blocks of whole rows, each downloaded into its place of the caller's arrays.
 constexpr long long kChunkPairs = 1LL << 24;
+// the alignment-free kernel needs no traceback arena and runs ~7000x more pairs per second: larger blocks (6.4 GB of results)
+constexpr long long kCountChunkPairs = 1LL << 27;
 
 int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
                     int32_t* out_score, int32_t* out_counts, double* out_metrics)
@@ -977,7 +979,7 @@ int taxi_count_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
     if (npairs == 0) return TAXI_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     flags &= ~(uint32_t)TAXI_OUT_SCORE;
-    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kCountChunkPairs / ny));
     if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
     for (int32_t r0 = 0; r0 < nx; r0 += rows) {
         const int32_t nr = std::min(rows, nx - r0);
@@ -1041,9 +1043,10 @@ int taxi_best_rows(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, 
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     if (nx == 0) return TAXI_OK;
     if (ny == 0) return fail(TAXI_E_ARG, "no columns to reduce over");
-    if (ny > kChunkPairs) return fail(TAXI_E_ARG, "too many columns for one device block (%d > %lld)", ny, kChunkPairs);
+    const long long chunk = align ? kChunkPairs : kCountChunkPairs;
+    if (ny > chunk) return fail(TAXI_E_ARG, "too many columns for one device block (%d > %lld)", ny, chunk);
     CUDA_TRY(cudaSetDevice(c->device));
-    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, chunk / ny));
     const uint32_t flags = TAXI_OUT_COUNTS | TAXI_OUT_METRICS;
     if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
     CUDA_TRY(c->d_argidx.reserve((size_t)rows));

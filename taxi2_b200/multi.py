@@ -176,6 +176,10 @@ class MultiEngine:
 
     # -- whole-matrix products -------------------------------------------------------------------------
     def _matrix(self, mode: str, want, rows_per_tile, pinned: bool, x_range=None, out: dict | None = None) -> dict:
+        if rows_per_tile is None and mode == "count":
+            # the alignment-free kernel does a row of barcodes in microseconds: one or two tiles per GPU
+            rows = (x_range[1] - x_range[0]) if x_range is not None else self.nx
+            rows_per_tile = max(1, min(-(-rows // (2 * len(self.engines))), (1 << 26) // max(self.ny, 1)))
         tiles = self.row_tiles(rows_per_tile, 1, x_range)
         x0 = tiles[0].x0 if tiles else 0
         nx, ny = sum(t.nx for t in tiles), self.ny
