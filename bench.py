@@ -465,6 +465,7 @@ def run_c3(args, rank: int, local_rank: int, world: int) -> None:
     if args.strong and n >= STRONG_Y:
         if rank == 0:
             strong = strong_scaling(data, off, world, debug)
+            torch.cuda.set_device(local_rank)
         if distributed:
             dist.barrier(group=host_group)
 

@@ -59,6 +59,23 @@ template <class T> struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Every entry point runs on its context's device and leaves the calling thread's current device
+// as it found it (the caller may be torch, or another context's thread).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                 \
+    DeviceGuard device_guard_(dev);    \
+    CUDA_TRY(device_guard_.err)
+
 struct SeqSet {
     bool loaded = false;
     int32_t n = 0;
@@ -418,7 +435,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
 
 int finish_align(taxi_ctx* c)
 {
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms += ms;
@@ -550,7 +567,7 @@ int taxi_ctx_create(int device, taxi_ctx** out)
     int n = 0;
     CUDA_TRY(cudaGetDeviceCount(&n));
     if (device < 0 || device >= n) return fail(TAXI_E_CUDA, "CUDA device %d not present (%d visible)", device, n);
-    CUDA_TRY(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(TAXI_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
@@ -571,7 +588,7 @@ int taxi_ctx_create(int device, taxi_ctx** out)
 void taxi_ctx_destroy(taxi_ctx* c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard device_guard_(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); s.span.release(); }
     c->d_codebook.release();
@@ -607,7 +624,7 @@ int taxi_set_scores(taxi_ctx* c, const int32_t s[TAXI_NSCORES])
 int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_t* offsets, int32_t n)
 {
     if (!c || (set != 0 && set != 1) || !offsets || n < 0) return fail(TAXI_E_ARG, "bad argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     SeqSet& s = c->set[set];
     s.loaded = false;
     s.off.assign(offsets, offsets + n + 1);
@@ -680,7 +697,7 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     int rc = check_ctx(c, true);
     if (rc) return rc;
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
     if (has_empty(c->set[0], x0, nx) || has_empty(yset(c), y0, ny))
@@ -807,7 +824,7 @@ int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
     const long long npairs = (long long)nx * ny;
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
     if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
     for (int32_t r0 = 0; r0 < nx; r0 += rows) {
@@ -829,7 +846,7 @@ int taxi_align_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t 
     reset_stats(c);
     if (npairs < 0 || (npairs > 0 && (!px || !py))) return fail(TAXI_E_ARG, "bad pair list");
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     int mr = 0, mc = 0;
     long long cells = 0;
     if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, &cells))) return rc;
@@ -873,7 +890,7 @@ int taxi_align_strings_metrics(taxi_ctx* c, const int32_t* px, const int32_t* py
     if (npairs < 0 || (npairs > 0 && (!px || !py || !aln_offsets || !out_x || !out_y || !aln_start)))
         return fail(TAXI_E_ARG, "bad argument");
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     int mr = 0, mc = 0;
     long long cells = 0;
     if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, &cells))) return rc;
@@ -960,7 +977,7 @@ int taxi_count_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CountArgs a{};
     a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.nx = nx; a.ny = ny; a.npairs = npairs;
     a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
@@ -977,7 +994,7 @@ int taxi_count_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
     if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
     const long long npairs = (long long)nx * ny;
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     flags &= ~(uint32_t)TAXI_OUT_SCORE;
     const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kCountChunkPairs / ny));
     if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
@@ -1000,7 +1017,7 @@ int taxi_count_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t 
     reset_stats(c);
     if (npairs < 0 || (npairs > 0 && (!px || !py))) return fail(TAXI_E_ARG, "bad pair list");
     if (npairs == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     int mr = 0, mc = 0;
     if ((rc = upload_pairs(c, px, py, npairs, &mr, &mc, nullptr, false))) return rc;
     if ((rc = reserve_outputs(c, npairs, flags & ~TAXI_OUT_SCORE))) return rc;
@@ -1019,7 +1036,7 @@ int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, in
     if (!c || !d_metrics || nx < 0 || ny <= 0 || metric < 0 || metric > 3 || !out_index_host)
         return fail(TAXI_E_ARG, "bad argument");
     if (nx == 0) return TAXI_OK;
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CUDA_TRY(c->d_argidx.reserve((size_t)nx));
     CUDA_TRY(c->d_argval.reserve((size_t)nx));
     const int wpb = 8;
@@ -1045,7 +1062,7 @@ int taxi_best_rows(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, 
     if (ny == 0) return fail(TAXI_E_ARG, "no columns to reduce over");
     const long long chunk = align ? kChunkPairs : kCountChunkPairs;
     if (ny > chunk) return fail(TAXI_E_ARG, "too many columns for one device block (%d > %lld)", ny, chunk);
-    CUDA_TRY(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, chunk / ny));
     const uint32_t flags = TAXI_OUT_COUNTS | TAXI_OUT_METRICS;
     if ((rc = reserve_outputs(c, (long long)rows * ny, flags))) return rc;
