@@ -5,6 +5,17 @@
 
 #define TAXI_FULL_MASK 0xffffffffu
 
+// Debug build (make bounds / -DTAXI_BOUNDS_CHECK): every access to the traceback arena, the
+// stripe-boundary buffer and the gapped-string slots is checked against its extent and a
+// violation sets the sticky device status (reported by the next taxi_sync as a TAXI_E_CUDA-class
+// error -90 - k).  compute-sanitizer is closed on the pool this was developed on; the GPU tests run
+// against this build instead (tools/bounds_check.sh).
+#ifdef TAXI_BOUNDS_CHECK
+#define TAXI_CHECK(a, cond, k) do { if (!(cond)) atomicMin((a).status, -90 - (k)); } while (0)
+#else
+#define TAXI_CHECK(a, cond, k) do { } while (0)
+#endif
+
 namespace taxi {
 
 // Values in the DP are score*64 + 6 tag bits.  The tag is the priority of the predecessor

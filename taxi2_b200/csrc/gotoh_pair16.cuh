@@ -113,13 +113,15 @@ __device__ __forceinline__ const uint8_t* trace_addr(const Walk& w, const uint8_
 }
 
 template <int H, bool MULTI>
-__device__ __forceinline__ void walk_fetch(Walk& w, int lane, const uint8_t* trace, int l0)
+__device__ __forceinline__ void walk_fetch(const AlignArgs& a, Walk& w, int lane, const uint8_t* trace, int l0)
 {
     const int di = (w.state != 2), dj = (w.state != 1);
     const int ii = w.i - lane * di, jj = w.j - lane * dj;
     w.tb = 0; w.ca = 0; w.cb = 0;
     if (w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1) {
-        w.tb = (int)__ldcg(trace_addr<H, MULTI>(w, trace, l0, ii, jj));
+        const uint8_t* at = trace_addr<H, MULTI>(w, trace, l0, ii, jj);
+        TAXI_CHECK(a, at >= trace && at < trace + a.trace_per_warp, 1);
+        w.tb = (int)__ldcg(at);
         w.ca = (int)__ldg(w.x + ii - 1);
         w.cb = (int)__ldg(w.y + jj - 1);
     }
@@ -173,6 +175,7 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
         w.pend += __popc(__ballot_sync(TAXI_FULL_MASK, k < 4) & visited);
     }
     if (a.aln_x != nullptr && mine) {
+        TAXI_CHECK(a, w.wpos - 1 - lane >= a.aln_off[w.p] && w.wpos - 1 - lane < a.aln_off[w.p + 1], 2);
         a.aln_x[w.wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : code_ascii(f, w.ca);
         a.aln_y[w.wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : code_ascii(f, w.cb);
     }
@@ -184,6 +187,7 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
 __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lane)
 {
     if (a.aln_x != nullptr) {
+        TAXI_CHECK(a, w.wpos - w.i - w.j >= a.aln_off[w.p] && w.wpos <= a.aln_off[w.p + 1], 3);
         // leading end gap: whatever is left of x (vertical) or y (horizontal)
         for (int k = lane; k < w.i; k += 32) {
             a.aln_x[w.wpos - 1 - k] = code_ascii(a.f16, (int)__ldg(w.x + w.i - 1 - k));
@@ -231,8 +235,8 @@ __device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, cons
 {
     if (!second) { wb.i = 0; wb.j = 0; }
     while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
-        walk_fetch<H, MULTI>(wa, lane, trace, l0);
-        walk_fetch<H, MULTI>(wb, lane, trace, l0);
+        walk_fetch<H, MULTI>(a, wa, lane, trace, l0);
+        walk_fetch<H, MULTI>(a, wb, lane, trace, l0);
         walk_advance(wa, a, lane);
         walk_advance(wb, a, lane);
     }
@@ -348,6 +352,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
                 outH = Hl[H - 1];
                 Hd_saved = rH;
                 uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+                TAXI_CHECK(a, reinterpret_cast<uint8_t*>(dst) >= trace && reinterpret_cast<uint8_t*>(dst) + HB <= trace + a.trace_per_warp, 4);
 #pragma unroll
                 for (int k = 0; k < HB / 16; ++k) {
                     uint32_t w[4];
@@ -484,6 +489,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 outH = Hl[H - 1];
                 Hd_saved = rH;
                 uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+                TAXI_CHECK(a, reinterpret_cast<uint8_t*>(dst) >= trace && reinterpret_cast<uint8_t*>(dst) + HB <= trace + a.trace_per_warp, 4);
 #pragma unroll
                 for (int k = 0; k < HB / 16; ++k) {
                     uint32_t w[4];
@@ -569,7 +575,10 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
         auto fetch_next = [&](int jj) {
             nb0 = (uint32_t)__ldg(A.yc + min(jj, A.nB + 1) - 1);
             nb1 = (uint32_t)__ldg(B.yc + min(jj, B.nB + 1) - 1);
-            if (lane == 0 && st > 0) { nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1); }   // lane 0: jj >= 1
+            if (lane == 0 && st > 0) {   // lane 0: jj >= 1
+                TAXI_CHECK(a, jj >= 0 && 2LL * jj + 1 < a.bnd_per_warp, 6);
+                nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1);
+            }
         };
         fetch_next(0 - (lane - first_lane) + 1);
 #pragma unroll 1
@@ -620,6 +629,7 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
                     outH = Hl[H - 1];
                     Hd_saved = rH;
                     uint4* dst = reinterpret_cast<uint4*>(tbase + (size_t)t * 32 * HB);
+                    TAXI_CHECK(a, reinterpret_cast<uint8_t*>(dst) >= trace && reinterpret_cast<uint8_t*>(dst) + HB <= trace + a.trace_per_warp, 5);
 #pragma unroll
                     for (int k = 0; k < HB / 16; ++k) {
                         uint32_t w[4];
@@ -628,6 +638,7 @@ __device__ __forceinline__ void align_two_bottom_multi(const AlignArgs& a, long 
                         __stcg(dst + k, make_uint4(w[0], w[1], w[2], w[3]));
                     }
                     if (lane == 31 && !last) {   // hand the stripe's bottom slot to the next stripe
+                        TAXI_CHECK(a, j >= 0 && 2LL * j + 1 < a.bnd_per_warp, 7);
                         __stcg(bnd + 2 * j, outX);
                         __stcg(bnd + 2 * j + 1, outH);
                     }

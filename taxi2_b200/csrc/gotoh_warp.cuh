@@ -111,7 +111,10 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
         auto fetch_next = [&](int jj) {
             if (live && jj >= 1 && jj <= nB) {
                 nb = (int)__ldg(y + jj - 1);
-                if (lane == 0 && s > 0) { nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1); }
+                if (lane == 0 && s > 0) {
+                    TAXI_CHECK(a, 2LL * jj + 1 < a.bnd_per_warp, 11);
+                    nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1);
+                }
             }
         };
         fetch_next(1 - lane);
@@ -167,6 +170,7 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                 outH = Hl[H - 1];
                 Hd_saved = rH;
                 uint8_t* dst = tbase + (size_t)t * 32 * HB;
+                TAXI_CHECK(a, dst >= trace && dst + HB <= trace + a.trace_per_warp, 12);
                 if constexpr (HB % 16 == 0) {
 #pragma unroll
                     for (int k = 0; k < HB / 16; ++k)
@@ -177,6 +181,7 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                         __stcg(reinterpret_cast<uint2*>(dst) + k, make_uint2(tw[2 * k], tw[2 * k + 1]));
                 }
                 if (lane == 31 && s + 1 < nstripes) {
+                    TAXI_CHECK(a, 2LL * j + 1 < a.bnd_per_warp, 13);
                     __stcg(bnd + 2 * j, outX);
                     __stcg(bnd + 2 * j + 1, outH);
                 }
@@ -214,6 +219,7 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
         if (valid) {
             const int q = (ii - 1) % SL;
             const int l = q / H, r = q % H, s = (ii - 1) / SL;
+            TAXI_CHECK(a, (long long)(((size_t)(s * step_stride + (jj - 1 + l)) * 32 + l) * HB + r) < a.trace_per_warp, 14);
             tb = (int)__ldcg(trace + ((size_t)(s * step_stride + (jj - 1 + l)) * 32 + l) * HB + r);
             ca = (int)__ldg(x + ii - 1);
             cb = (int)__ldg(y + jj - 1);
@@ -250,6 +256,7 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
             pend += __popc(gm);
         }
         if (strings && lane < V) {
+            TAXI_CHECK(a, wpos - 1 - lane >= a.aln_off[p] && wpos - 1 - lane < a.aln_off[p + 1], 15);
             a.aln_x[wpos - 1 - lane] = (state == 2) ? (uint8_t)'-' : (uint8_t)ca;
             a.aln_y[wpos - 1 - lane] = (state == 1) ? (uint8_t)'-' : (uint8_t)cb;
         }
