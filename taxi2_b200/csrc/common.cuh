@@ -186,7 +186,7 @@ __device__ __forceinline__ double log_pos(double x)   // log(x), x > 0 normal (f
     const double f = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x)) - 1.0;
     const double t = 2.0 + f;
     const double s = div_by(f, t, rcp_full(t));
-    const double dk = (double)k;
+    const double dk = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;   // (double)k without I2F: 2^52 + 2^31 + k, minus both
     const double z = s * s, w = z * z;
     const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
     const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
@@ -195,18 +195,25 @@ __device__ __forceinline__ double log_pos(double x)   // log(x), x > 0 normal (f
     return fma(dk, kLogCoef[7], -((hfsq - fma(s, hfsq + R, dk * kLogCoef[8])) - f));
 }
 
+// exact int -> double for 0 <= k < 2^31 without the XU-pipe I2F (which shares a quarter-rate pipe
+// with POPC and MUFU): 2^52 + k assembled as bits, minus 2^52
+__device__ __forceinline__ double count_to_double(int k)
+{
+    return __hiloint2double(0x43300000, k) - 4503599627370496.0;
+}
+
 // distances.py:319-348 formulas in fp64; NaN where the reference yields None.
 __device__ __forceinline__ void metrics_from_counts(int same, int ts, int tv, int gap, double out[4])
 {
-    const double n = (double)(same + ts + tv);
+    const double n = count_to_double(same + ts + tv);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     if (!(n > 0.0)) { out[0] = out[1] = out[2] = out[3] = nan; return; }
-    const double d = (double)(ts + tv), g = (double)gap;
+    const double d = count_to_double(ts + tv), g = count_to_double(gap);
     const double rn = rcp_full(n);
     const double p = div_by(d, n, rn);
     out[0] = p;
     out[1] = div_by(d + g, n + g, rcp_full(n + g));
-    const double P = div_by((double)ts, n, rn), Q = div_by((double)tv, n, rn);
+    const double P = div_by(count_to_double(ts), n, rn), Q = div_by(count_to_double(tv), n, rn);
     const double u = 1.0 - div_by(4.0 * p, 3.0, 1.0 / 3.0);           // jc = -3/4 ln(1 - 4p/3)
     const double b = 1.0 - 2.0 * Q, a = 1.0 - 2.0 * P - Q;             // k2p = -1/2 ln((1 - 2P - Q) sqrt(1 - 2Q))
     const double v = (a > 0.0 && b > 0.0) ? a * sqrt_pos(b) : -1.0;

@@ -6,7 +6,9 @@ Tabfile :32-48, Formatted :51-97).
 from __future__ import annotations
 
 from pathlib import Path
-from typing import NamedTuple, TextIO
+from typing import Iterator, NamedTuple
+
+import numpy as np
 
 from .handlers import FileHandler, ReadHandle, WriteHandle
 from .sequences import Sequence, Sequences
@@ -33,58 +35,73 @@ class SequencePairHandler(FileHandler[SequencePair]):
     pass
 
 
+PAIR_COLUMNS = ("idx", "idy", "seqx", "seqy")
+
+
+def match_pattern(x: str, y: str) -> str:
+    """The middle line of a formatted pair (pairs.py:52-58): '-' where either string has a gap,
+    '|' where the two symbols are equal, '.' elsewhere.  Compared as bytes in one numpy pass
+    (aligned barcodes are hundreds of columns; the reference maps a Python function over them)."""
+    a = np.frombuffer(x.encode("latin-1", "replace"), dtype=np.uint8)
+    b = np.frombuffer(y.encode("latin-1", "replace"), dtype=np.uint8)
+    n = min(len(a), len(b))          # map() over two strings stops at the shorter one
+    a, b = a[:n], b[:n]
+    out = np.full(n, ord("."), dtype=np.uint8)
+    out[a == b] = ord("|")
+    out[(a == ord("-")) | (b == ord("-"))] = ord("-")
+    return out.tobytes().decode("latin-1")
+
+
+def _records(path: Path) -> Iterator[list[str]]:
+    """Blocks of stripped lines of a formatted pairs file, five lines apiece (the fifth is the
+    separator); the file ends at the first block that is entirely empty."""
+    with open(path, "r") as file:
+        while True:
+            block = [file.readline().strip() for _ in range(5)]
+            if not any(block):
+                return
+            yield block
+
+
 class Tabfile(SequencePairHandler):
+    """idx / idy / seqx / seqy, tab separated, one header row (pairs.py:32-48)."""
+
     def _iter_read(self) -> ReadHandle[SequencePair]:
-        with FileHandler.Tabfile(self.path, "r", has_headers=True) as file:
+        with FileHandler.Tabfile(self.path, "r", has_headers=True) as rows:
             yield self
-            for idx, idy, seqX, seqY in file:
-                yield SequencePair(Sequence(idx, seqX), Sequence(idy, seqY))
+            for row in rows:
+                id_x, id_y, seq_x, seq_y = row
+                yield SequencePair(x=Sequence(id_x, seq_x), y=Sequence(id_y, seq_y))
 
     def _iter_write(self) -> WriteHandle[SequencePair]:
-        with FileHandler.Tabfile(self.path, "w", columns=["idx", "idy", "seqx", "seqy"]) as file:
+        with FileHandler.Tabfile(self.path, "w", columns=list(PAIR_COLUMNS)) as rows:
             try:
                 while True:
-                    pair = yield
-                    file.write((pair.x.id, pair.y.id, pair.x.seq, pair.y.seq))
+                    x, y = yield
+                    rows.write((x.id, y.id, x.seq, y.seq))
             except GeneratorExit:
-                return
+                pass
 
 
 class Formatted(SequencePairHandler):
-    """Four-line blocks: 'idx / idy', aligned x, match pattern, aligned y; blank line between."""
+    """Four-line records -- 'idx / idy', aligned x, match pattern, aligned y -- separated by one
+    empty line (pairs.py:51-97)."""
 
-    @staticmethod
-    def _format_char(x: str, y: str) -> str:
-        if x == "-" or y == "-":
-            return "-"
-        return "|" if x == y else "."
-
-    @classmethod
-    def _format(cls, x: str, y: str) -> str:
-        return "".join(map(cls._format_char, x, y))
+    _format = staticmethod(match_pattern)
 
     def _iter_read(self) -> ReadHandle[SequencePair]:
-        with open(self.path, "r") as file:
-            yield self
-            while True:
-                lines = [file.readline().strip() for _ in range(5)]
-                if not any(lines):
-                    return
-                idx, idy = lines[0].split(" / ")
-                yield SequencePair(Sequence(idx, lines[1]), Sequence(idy, lines[3]))
+        yield self
+        for title, seq_x, _pattern, seq_y, _blank in _records(self.path):
+            id_x, id_y = title.split(" / ")
+            yield SequencePair(x=Sequence(id_x, seq_x), y=Sequence(id_y, seq_y))
 
     def _iter_write(self) -> WriteHandle[SequencePair]:
         with open(self.path, "w") as file:
+            separator = ""
             try:
-                first = True
                 while True:
-                    pair = yield
-                    if not first:
-                        file.write("\n")
-                    first = False
-                    self._write_lines(file, pair)
+                    x, y = yield
+                    file.write(f"{separator}{x.id} / {y.id}\n{x.seq}\n{match_pattern(x.seq, y.seq)}\n{y.seq}\n")
+                    separator = "\n"
             except GeneratorExit:
-                return
-
-    def _write_lines(self, file: TextIO, pair: SequencePair) -> None:
-        file.write(f"{pair.x.id} / {pair.y.id}\n{pair.x.seq}\n{self._format(pair.x.seq, pair.y.seq)}\n{pair.y.seq}\n")
+                pass

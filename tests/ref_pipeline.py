@@ -1,7 +1,11 @@
 """Per-pair restatement of the reference's task pipelines for the parity tests (test
 infrastructure): the same generator order as /root/reference/src/itaxotools/taxi2/tasks/
 versus_all.py:732-773 and versus_reference.py:213-247, with the two native calls answered by the
-CPU oracle.  Deliberately written pair-at-a-time, independent of taxi2_b200.tasks."""
+CPU oracle.  Deliberately written pair-at-a-time, independent of taxi2_b200.tasks AND of the
+package's file handlers: every output file is written by the small plain-text writers below,
+restated from the reference's writer code, so a "want" tree never passes
+through the code under test.  (The package's handlers are pinned separately, against the
+reference's own fixture files, in tests/test_host_api.py.)"""
 from __future__ import annotations
 
 from itertools import groupby
@@ -9,10 +13,133 @@ from math import inf, isnan
 from pathlib import Path
 
 import oracle
-from taxi2_b200.distances import Distance, DistanceHandler, DistanceMetric
-from taxi2_b200.handlers import FileHandler
-from taxi2_b200.pairs import SequencePair, SequencePairHandler
+from taxi2_b200.distances import Distance, DistanceMetric
+from taxi2_b200.pairs import SequencePair
 from taxi2_b200.sequences import Sequence
+
+
+class PlainTab:
+    """handlers.py:219-227: "\\t".join(row) + "\\n", LF endings, no quoting; optional header row."""
+
+    def __init__(self, path, mode="w", columns=None):
+        self.file = open(path, "w", newline="")
+        if columns:
+            self.write(columns)
+
+    def write(self, row):
+        self.file.write("\t".join(str(v) for v in row) + "\n")
+
+    def close(self):
+        self.file.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class PlainLinear(PlainTab):
+    """distances.py:75-130, 244-279: one row per run of distances with the same (x.id, y.id);
+    header from the first row: seqid (query), <extras> (query), seqid (reference), <extras>
+    (reference), metric labels; None -> missing."""
+
+    def __init__(self, path, mode="w", missing="NA", formatter="{:.4f}", tag_x=" (query)", tag_y=" (reference)"):
+        super().__init__(path)
+        self.missing, self.formatter, self.tags = missing, formatter, (tag_x, tag_y)
+        self.run, self.header_done = [], False
+
+    def write(self, distance):
+        if self.run and (self.run[0].x.id, self.run[0].y.id) != (distance.x.id, distance.y.id):
+            self.flush()
+        self.run.append(distance)
+
+    def flush(self):
+        if not self.run:
+            return
+        x, y = self.run[0].x, self.run[0].y
+        if not self.header_done:
+            PlainTab.write(self, ["seqid" + self.tags[0], *(k + self.tags[0] for k in x.extras), "seqid" + self.tags[1],
+                                  *(k + self.tags[1] for k in y.extras), *(str(d.metric) for d in self.run)])
+            self.header_done = True
+        text = lambda v: self.missing if v is None else self.formatter.format(v)  # noqa: E731
+        fill = lambda v: self.missing if v is None else v  # noqa: E731
+        PlainTab.write(self, [x.id, *map(fill, x.extras.values()), y.id, *map(fill, y.extras.values()), *(text(d.d) for d in self.run)])
+        self.run = []
+
+    def close(self):
+        self.flush()
+        super().close()
+
+
+class PlainMatrix(PlainTab):
+    """distances.py:143-186: one row per run of distances with the same x.id: x.id, scores; the
+    header (an empty cell, then the y ids of the first row) precedes the first row."""
+
+    def __init__(self, path, mode="w", missing="NA", formatter="{:.4f}"):
+        super().__init__(path)
+        self.missing, self.formatter = missing, formatter
+        self.run, self.header_done = [], False
+
+    def write(self, distance):
+        if self.run and self.run[0].x.id != distance.x.id:
+            self.flush()
+        self.run.append(distance)
+
+    def flush(self):
+        if not self.run:
+            return
+        if not self.header_done:
+            PlainTab.write(self, ["", *(d.y.id for d in self.run)])
+            self.header_done = True
+        PlainTab.write(self, [self.run[0].x.id, *(self.missing if d.d is None else self.formatter.format(d.d) for d in self.run)])
+        self.run = []
+
+    def close(self):
+        self.flush()
+        super().close()
+
+
+class PlainPairs:
+    """pairs.py:51-97: 'idx / idy', aligned x, pattern ('-' if either is a gap, '|' if equal, '.'
+    otherwise), aligned y; one empty line between records."""
+
+    def __init__(self, path, mode="w"):
+        self.file = open(path, "w", newline="")
+        self.first = True
+
+    def write(self, pair):
+        pattern = "".join("-" if "-" in (a, b) else ("|" if a == b else ".") for a, b in zip(pair.x.seq, pair.y.seq))
+        self.file.write(("" if self.first else "\n") + f"{pair.x.id} / {pair.y.id}\n{pair.x.seq}\n{pattern}\n{pair.y.seq}\n")
+        self.first = False
+
+    def close(self):
+        self.file.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class _Plain:
+    """Stand-ins with the handler names the pipelines below were written against."""
+
+    class FileHandler:
+        Tabfile = PlainTab
+
+    class DistanceHandler:
+        Matrix = PlainMatrix
+
+        class Linear:
+            WithExtras = PlainLinear
+
+    class SequencePairHandler:
+        Formatted = PlainPairs
+
+
+FileHandler, DistanceHandler, SequencePairHandler = _Plain.FileHandler, _Plain.DistanceHandler, _Plain.SequencePairHandler
 
 LABELS = ["p", "p-gaps", "jc", "k2p"]
 
@@ -226,13 +353,54 @@ def versus_reference(data, reference, work: Path, align=True, metric=None, extra
 
 
 # ---- dereplicate / decontaminate (dereplicate.py:393-440, decontaminate.py:336-371, decontaminate2.py) ----
-from taxi2_b200.sequences import SequenceHandler  # noqa: E402
+class PlainSequenceTab(PlainTab):
+    """sequences.py:211-234 with idHeader="seqid", seqHeader="sequence": header seqid, <extras>,
+    sequence from the first record (seqid, sequence alone for an empty file), then one row each."""
+
+    def __init__(self, path):
+        super().__init__(path)
+        self.header_done = False
+
+    def write(self, sequence):
+        if not self.header_done:
+            PlainTab.write(self, ["seqid", *sequence.extras.keys(), "sequence"])
+            self.header_done = True
+        PlainTab.write(self, [sequence.id, *sequence.extras.values(), sequence.seq])
+
+    def close(self):
+        if not self.header_done:
+            PlainTab.write(self, ["seqid", "sequence"])
+        super().close()
+
+
+class PlainFasta:
+    """sequences.py:97-114 with write_organism=True: ">id|organism" (the organism only when the
+    record has one), the sequence in 60-column lines, one empty line after every record."""
+
+    def __init__(self, path):
+        self.file = open(path, "w", newline="")
+
+    def write(self, sequence):
+        title = sequence.id
+        if organism := sequence.extras.get("organism", None):
+            title += "|" + organism
+        self.file.write(">" + title + "\n")
+        for k in range(0, len(sequence.seq), 60):
+            self.file.write(sequence.seq[k:k + 60] + "\n")
+        self.file.write("\n")
+
+    def close(self):
+        self.file.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def _out_handler(path: Path, fasta: bool):
-    if fasta:
-        return SequenceHandler.Fasta(path, "w", write_organism=True)
-    return SequenceHandler.Tabfile(path, "w", idHeader="seqid", seqHeader="sequence")
+    return PlainFasta(path) if fasta else PlainSequenceTab(path)
 
 
 def dereplicate(sequences, work: Path, similarity=0.07, length=10, align=True, metric=None, fmt="{:.4f}", missing="NA",

@@ -70,3 +70,43 @@ def test_versus_reference_blocks_over_several_engines(tmp_path, monkeypatch, eng
     task.start()
     ref_pipeline.versus_reference(data, reference, tmp_path / "want")
     assert tree(task.work_dir) == tree(tmp_path / "want")
+
+
+@pytest.mark.parametrize("align,multiply,fasta,native", [(True, False, False, True), (True, True, True, False), (False, False, True, True)])
+def test_decontaminate_blocks_over_several_engines(tmp_path, monkeypatch, align, multiply, fasta, native):
+    from taxi2_b200.files import FileFormat
+    from taxi2_b200.tasks import Decontaminate, Decontaminate2, decontaminate
+
+    seqs, _, _ = load("Taxi2test1_50.tab")
+    records = short(list(seqs))
+    data, outgroup, ingroup = records[:10], records[10:22], records[22:34]
+    data.append(Sequence("allN", "nnnnnnnn", records[0].extras))
+    multi = oracle_multi(3)
+    monkeypatch.setattr(decontaminate, "task_engine", lambda task: multi)
+    monkeypatch.setattr(common, "MAX_BLOCK_PAIRS", 30)
+    task = Decontaminate()
+    task.work_dir = tmp_path / "got1"
+    task.native_writers = native
+    task.progress_handler = lambda *a: None
+    task.input, task.outgroup = Sequences(data), Sequences(outgroup)
+    task.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
+    task.params.pairs.align = align
+    task.params.format.percentage_multiply = multiply
+    task.params.thresholds.similarity = 12.0 if multiply else 0.12
+    task.start()
+    ref_pipeline.decontaminate(data, outgroup, tmp_path / "want1", similarity=task.params.thresholds.similarity, align=align,
+                               multiply=multiply, fasta=fasta)
+    assert tree(task.work_dir) == tree(tmp_path / "want1")
+
+    task2 = Decontaminate2()
+    task2.work_dir = tmp_path / "got2"
+    task2.native_writers = native
+    task2.progress_handler = lambda *a: None
+    task2.input, task2.outgroup, task2.ingroup = Sequences(data), Sequences(outgroup), Sequences(ingroup)
+    task2.output_format = FileFormat.Fasta if fasta else FileFormat.Tabfile
+    task2.params.pairs.align = align
+    task2.params.format.percentage_multiply = multiply
+    task2.params.weights.outgroup, task2.params.weights.ingroup = 1.0, 1.5
+    task2.start()
+    ref_pipeline.decontaminate2(data, outgroup, ingroup, tmp_path / "want2", w_out=1.0, w_in=1.5, align=align, multiply=multiply, fasta=fasta)
+    assert tree(task2.work_dir) == tree(tmp_path / "want2")
