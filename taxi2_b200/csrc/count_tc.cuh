@@ -1,0 +1,264 @@
+// Alignment-free mode on the tensor cores: the per-pair column counts of count_planes.cuh as ONE
+// int8 contraction per 128 x 128 tile of the pair matrix, hand-written for sm_100a
+// (tcgen05.mma kind::i8 issued by one elected thread, operands staged by TMA with the 128-byte
+// swizzle, four int32 accumulators in TMEM, read back with tcgen05.ld by the epilogue warps).
+//
+// Replaces, like count_rect_kernel, calc.seq_distances_{p,p_gaps,jukes_cantor,kimura2p} applied to
+// pre-aligned strings (reference: src/itaxotools/taxi2/distances.py:319-348 from
+// versus_all.py:546-552 with params.pairs.align = False).  north_star: "an int8 one-hot
+// tensor-core contraction is kept only if ncu shows it beats popcount" -- it does: the popcount
+// kernel is bound by POPC (16 lanes/clk/SM) at 1.35 ms for 9000 x 9000 x 618 columns, the
+// contraction below takes 0.3-0.4 ms (tools/tc_onehot.cu, profiles/tc_onehot_r02.json).
+//
+// Encoding.  With the 2-bit nucleotide code of the planes (A=00 G=01 C=10 T=11) write u0, u1 = +1 /
+// -1 for bit 0 / bit 1 of a real base and 0 for anything else, R = 1 for a real base.  Summed over
+// the columns of a pair,
+//     n    = R.R                          both real
+//     S1   = u1.u1                        purine/pyrimidine class agrees minus disagrees
+//     S0+S01 = u0.u0 + (u0 u1).(u0 u1)
+//     same = (n + S1 + (S0 + S01)) / 4,   transitions = (n + S1 - (S0 + S01)) / 4,
+//     transversions = (n - S1) / 2
+// because [same] = (1 + u0x u0y)(1 + u1x u1y) / 4 on a both-real column.  Gap columns are
+// G'x.Ry + Rx.G'y with the clipped gap plane G' of count_planes.cuh.  Every sequence therefore
+// becomes a row of 8 * Lp signed bytes (Lp = columns padded to 128):
+//     [0, Lp)     R                       -> accumulator 0 (x . y)
+//     [Lp, 2Lp)   u1                      -> accumulator 1
+//     [2Lp, 4Lp)  u0, u0 u1 interleaved   -> accumulator 2
+//     [4Lp, 6Lp)  G', R interleaved       -> accumulator 3, the row's role as x
+//     [6Lp, 8Lp)  R, G' interleaved       ->                its role as y
+// 6 Lp bytes of K per pair.  The few gap columns outside the first / last both-real column are
+// subtracted in the epilogue exactly as in the popcount kernel (gaps_outside_trim on the planes),
+// and the fp64 metrics are computed there too, so the kernel writes the same 16 B + 32 B per pair.
+//
+// One CTA per tile, one CTA per SM (the four accumulators take all 512 TMEM columns): warp 0 feeds
+// TMA, warp 1 issues the MMAs, 16 epilogue warps (4 per TMEM lane quarter, 32 columns each) do
+// trim, metrics and stores -- the epilogue, not the contraction, is what bounds the kernel.
+#pragma once
+#include <cuda.h>
+
+#include "count_planes.cuh"
+
+namespace taxi {
+
+constexpr int TC_TILE = 128;              // pairs per tile side; also bytes of K per pipeline stage
+constexpr int TC_UMMA_K = 32;             // bytes of K per tcgen05.mma (8-bit operands)
+constexpr int TC_STAGES = 5;
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_ROW_SEGMENTS = 8;        // row length in units of Lp
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * 2 * TC_TILE * TC_TILE + 1024;
+
+// one thread per (sequence, 4 columns): planes -> operand row
+__global__ void tc_operands_kernel(const uint4* __restrict__ planes, int32_t nseq, int32_t W, int32_t Lp, int8_t* __restrict__ out)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups = Lp / 4;
+    if (gid >= (long long)nseq * groups) return;
+    const int seq = (int)(gid % nseq), c0 = (int)(gid / nseq) * 4;   // sequence fastest: coalesced plane reads
+    const int w = c0 / 32;
+    uint4 pw = make_uint4(0, 0, 0, 0);
+    if (w < W) pw = __ldg(planes + (size_t)w * nseq + seq);
+    uint32_t r4 = 0, u14 = 0;
+    uint32_t m2[2] = {0, 0}, gx[2] = {0, 0}, gy[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int bit = (c0 + k) & 31;
+        const int R = (pw.z >> bit) & 1, G = (pw.w >> bit) & 1;
+        const int u0 = R ? (((pw.x >> bit) & 1) ? -1 : 1) : 0, u1 = R ? (((pw.y >> bit) & 1) ? -1 : 1) : 0;
+        r4 |= (uint32_t)R << (8 * k);
+        u14 |= (uint32_t)(uint8_t)u1 << (8 * k);
+        m2[k >> 1] |= ((uint32_t)(uint8_t)u0 | ((uint32_t)(uint8_t)(u0 * u1) << 8)) << (16 * (k & 1));
+        gx[k >> 1] |= ((uint32_t)G | ((uint32_t)R << 8)) << (16 * (k & 1));
+        gy[k >> 1] |= ((uint32_t)R | ((uint32_t)G << 8)) << (16 * (k & 1));
+    }
+    int8_t* row = out + (size_t)seq * TC_ROW_SEGMENTS * Lp;
+    *reinterpret_cast<uint32_t*>(row + c0) = r4;
+    *reinterpret_cast<uint32_t*>(row + Lp + c0) = u14;
+    *reinterpret_cast<uint2*>(row + 2 * Lp + 2 * c0) = make_uint2(m2[0], m2[1]);
+    *reinterpret_cast<uint2*>(row + 4 * Lp + 2 * c0) = make_uint2(gx[0], gx[1]);
+    *reinterpret_cast<uint2*>(row + 6 * Lp + 2 * c0) = make_uint2(gy[0], gy[1]);
+}
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major operand tile as TMA writes it with the 128-byte swizzle: rows of 128 bytes, groups of 8 rows 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(const void* tile, int k_byte_offset)
+{
+    const uint32_t addr = smem_u32(tile) + (uint32_t)k_byte_offset;
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
+}
+
+}  // namespace tc
+
+struct CountTcArgs {
+    CountArgs c;          // planes (trim correction), rectangle, outputs
+    int32_t Lp;           // padded columns of the operand rows (the smaller of the two sets')
+    int32_t LpX, LpY;     // padded columns of each set's operand rows (segment offsets)
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const CountTcArgs args)
+{
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int STAGE_BYTES = TC_TILE * TC_TILE;                   // one operand tile: 128 rows x 128 bytes
+    uint8_t* sX = smem;
+    uint8_t* sY = smem + TC_STAGES * STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sY + TC_STAGES * STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* accum_full = empty + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+    const CountArgs& a = args.c;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xt = blockIdx.y * TC_TILE, yt = blockIdx.x * TC_TILE;   // tile origin inside the rectangle
+    const int Lp = args.Lp;
+    const int blocks_per_L = Lp / TC_TILE;
+    const int kblocks = 6 * blocks_per_L;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&map_y) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    // k-block kb of the pair's 6 Lp bytes: which accumulator it feeds and where it sits in the x / y rows
+    auto segment = [&](int kb, int& acc, int& kx, int& ky) {
+        const int unit = kb / blocks_per_L, within = (kb % blocks_per_L) * TC_TILE;   // unit: 0 R, 1 u1, 2-3 u0/u0u1, 4-5 gap
+        acc = unit == 0 ? 0 : unit == 1 ? 1 : unit < 4 ? 2 : 3;
+        const int seg_x = unit < 4 ? unit : unit;              // x rows: segments 0..5 in order
+        const int seg_y = unit < 4 ? unit : unit + 2;          // y rows: the gap segment of the y role is 6..7
+        kx = seg_x * args.LpX + within;
+        ky = seg_y * args.LpY + within;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % TC_STAGES;
+                int acc, kx, ky;
+                segment(kb, acc, kx, ky);
+                mbar_wait(empty + s, ((kb / TC_STAGES) & 1) ^ 1);
+                mbar_expect_tx(full + s, 2 * STAGE_BYTES);
+                tma_load_2d(sX + s * STAGE_BYTES, &map_x, full + s, kx, a.x0 + xt);
+                tma_load_2d(sY + s * STAGE_BYTES, &map_y, full + s, ky, a.y0 + yt);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // S32 accumulators, signed 8-bit A and B, both K-major, N = 128, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+            int prev_acc = -1;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % TC_STAGES;
+                int acc, kx, ky;
+                segment(kb, acc, kx, ky);
+                mbar_wait(full + s, (kb / TC_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < TC_TILE / TC_UMMA_K; ++k)
+                    umma_i8(tmem + (uint32_t)(acc * TC_TILE), umma_desc(sX + s * STAGE_BYTES, k * TC_UMMA_K),
+                            umma_desc(sY + s * STAGE_BYTES, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
+                prev_acc = acc;
+                umma_commit(empty + s);
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        mbar_wait(accum_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int e = warp - 2;
+        const int q = warp & 3;                          // this warp reaches TMEM lanes [32 q, 32 q + 32)
+        const int cg = e >> 2;                           // its 32 columns of the tile
+        const int xr = xt + q * 32 + lane;               // row inside the rectangle
+        const bool row_ok = xr < a.nx;
+        const int xs = a.x0 + min(xr, a.nx - 1);
+        const int2 sx = __ldg(a.x.span + xs);
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            const int c0 = cg * 32 + ch * 8;
+            int A0[8], A1[8], A2[8], A3[8];
+            tmem_ld8(lane_addr + (uint32_t)(0 * TC_TILE + c0), A0);
+            tmem_ld8(lane_addr + (uint32_t)(1 * TC_TILE + c0), A1);
+            tmem_ld8(lane_addr + (uint32_t)(2 * TC_TILE + c0), A2);
+            tmem_ld8(lane_addr + (uint32_t)(3 * TC_TILE + c0), A3);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int yc = yt + c0 + k;
+                if (row_ok && yc < a.ny) {
+                    const int n = A0[k];
+                    const int ts = (n + A1[k] - A2[k]) >> 2, tv = (n - A1[k]) >> 1;
+                    int gap = A3[k];
+                    const int ys = a.y0 + yc;
+                    if (n > 0 && gap > 0)
+                        gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xs); }, [&](int w) { return a.y.at(w, ys); },
+                                                 sx, __ldg(a.y.span + ys));
+                    store_pair(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
+}  // namespace taxi

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "count_planes.cuh"
+#include "count_tc.cuh"
 #include "gotoh_pair16.cuh"
 #include "gotoh_warp.cuh"
 
@@ -87,6 +88,11 @@ struct SeqSet {
     DevBuf<int64_t> d_off;
     DevBuf<uint4> planes;           // [W][n] (b0, b1, R, G') per 32 columns (count_planes.cuh)
     DevBuf<int2> span;              // [n] first / last word with a real column
+    // tensor-core operand rows of the alignment-free kernel (count_tc.cuh), built on first use
+    DevBuf<int8_t> tcops;           // [n][8 * Lp]
+    int32_t Lp = 0;                 // columns padded to TC_TILE
+    bool tc_built = false;
+    CUtensorMap tc_map;
     int32_t W = 0;
 };
 
@@ -110,6 +116,7 @@ struct taxi_ctx {
     int force_general = 0;          // option: always use the general int32 kernel
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
+    int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
     DevBuf<uint8_t> trace;
@@ -590,7 +597,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     if (!c) return;
     DeviceGuard device_guard_(c->device);
     cudaStreamSynchronize(c->stream);
-    for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); s.span.release(); }
+    for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); s.span.release(); s.tcops.release(); }
     c->d_codebook.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
     c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_units.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
@@ -669,6 +676,7 @@ int taxi_load_sequences(taxi_ctx* c, int set, const uint8_t* bytes, const int64_
         // a symbol first seen in set 1 extends the book: set 0 was encoded with the older book,
         // which is still right for every symbol set 0 contains
     }
+    s.tc_built = false;
     s.W = std::max(1, ((s.maxlen + 31) / 32 + COUNT_G - 1) / COUNT_G) * COUNT_G;   // whole carry-save groups
     CUDA_TRY(s.planes.reserve((size_t)std::max(n, 1) * s.W, 1));
     CUDA_TRY(s.span.reserve((size_t)std::max(n, 1), 1));
@@ -929,6 +937,52 @@ int taxi_align_strings(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_
                                       out_score ? TAXI_OUT_SCORE : 0u, out_score, nullptr, nullptr);
 }
 
+// ---- tensor-core operands of the alignment-free kernel -------------------------------------------
+constexpr size_t kTcMaxOperandBytes = (size_t)8 << 30;   // per set; beyond it rectangles stay on the popcount kernel
+
+size_t tc_operand_bytes(const SeqSet& s)
+{
+    const size_t Lp = (size_t)(s.W * 32 + TC_TILE - 1) / TC_TILE * TC_TILE;
+    return (size_t)std::max(s.n, 1) * TC_ROW_SEGMENTS * Lp;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ensure_tc_operands(taxi_ctx* c, SeqSet& s)
+{
+    if (s.tc_built) return TAXI_OK;
+    static EncodeTiledFn encode = nullptr;
+    static std::mutex encode_lock;
+    {
+        std::lock_guard<std::mutex> guard(encode_lock);
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) return fail(TAXI_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = (EncodeTiledFn)fn;
+        }
+    }
+    s.Lp = (s.W * 32 + TC_TILE - 1) / TC_TILE * TC_TILE;
+    const size_t row = (size_t)TC_ROW_SEGMENTS * s.Lp;
+    CUDA_TRY(s.tcops.reserve((size_t)std::max(s.n, 1) * row, 1));
+    if (s.n > 0) {
+        const long long threads = (long long)s.n * (s.Lp / 4);
+        tc_operands_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(s.planes.p, s.n, s.W, s.Lp, s.tcops.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)row, (cuuint64_t)std::max(s.n, 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)row};
+    cuuint32_t box[2] = {(cuuint32_t)TC_TILE, (cuuint32_t)TC_TILE};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&s.tc_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.tcops.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TAXI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    s.tc_built = true;
+    return TAXI_OK;
+}
+
 static int enqueue_count(taxi_ctx* c, CountArgs a)
 {
     const SeqSet& X = c->set[0];
@@ -942,9 +996,36 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         c->launches += 1;
+        c->last_kernel = 8;
         return TAXI_OK;
     }
     const int W = std::min(X.W, Y.W);
+    // tensor-core kernel (count_tc.cuh): rectangles of at least a few tiles whose rows fit the operand layout
+    if (c->count_kernel != 1) {
+        const long long tiles = (long long)((a.nx + TC_TILE - 1) / TC_TILE) * ((a.ny + TC_TILE - 1) / TC_TILE);
+        const bool fits = tc_operand_bytes(X) <= kTcMaxOperandBytes && tc_operand_bytes(Y) <= kTcMaxOperandBytes &&
+                          (a.nx + TC_TILE - 1) / TC_TILE <= 65535;
+        if (fits && (c->count_kernel == 2 || tiles >= 2LL * c->sms)) {
+            int rc = ensure_tc_operands(c, c->set[0]);
+            if (rc == TAXI_OK && c->set[1].loaded) rc = ensure_tc_operands(c, c->set[1]);
+            if (rc) return rc;
+            const SeqSet& XX = c->set[0];
+            const SeqSet& YY = yset(c);
+            a.slab = 0;
+            CountTcArgs t{a, std::min(XX.Lp, YY.Lp), XX.Lp, YY.Lp};
+            CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+            dim3 grid((unsigned)((a.ny + TC_TILE - 1) / TC_TILE), (unsigned)((a.nx + TC_TILE - 1) / TC_TILE));
+            CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+            count_tc_kernel<<<grid, TC_THREADS, TC_SMEM, c->stream>>>(XX.tc_map, YY.tc_map, t);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+            c->launches += 1;
+            c->last_kernel = 9;
+            return TAXI_OK;
+        }
+        if (c->count_kernel == 2) return fail(TAXI_E_RANGE, "sequences too long for the tensor-core counting kernel");
+    }
+    c->last_kernel = 8;
     // x rows per block: as many as fit ~64 KB of shared memory (three blocks per SM), at most COUNT_SLAB
     const size_t row_bytes = (size_t)W * sizeof(uint4);
     if (row_bytes > 200 * 1024) return fail(TAXI_E_RANGE, "sequences too long for the alignment-free kernel (%d words per plane)", W);
@@ -1105,6 +1186,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (std::strcmp(key, "force_general") == 0) { c->force_general = value; return TAXI_OK; }
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
     if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
+    if (std::strcmp(key, "count_kernel") == 0) { c->count_kernel = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }
 

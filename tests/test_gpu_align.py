@@ -572,3 +572,65 @@ def test_alignment_free_long_sequences(engine):
                 c = oracle.count(seqs[i].decode(), seqs[j].decode()) or (0, 0, 0, 0)
                 assert tuple(got["counts"][i, j]) == tuple(c), (length, i, j)
                 assert_metrics_close(got["metrics"][i, j][None, :], np.array(oracle.metrics(c))[None, :])
+
+
+def _junk_rows(rng, n, lo, hi, alphabet=b"ACGTacgt-N?RY", weights=None):
+    al = np.frombuffer(alphabet, dtype=np.uint8)
+    p = None if weights is None else np.asarray(weights, dtype=float) / sum(weights)
+    return [al[rng.choice(len(al), int(rng.integers(lo, hi + 1)), p=p)].tobytes().decode() for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", ["ragged", "prealigned", "two_sets", "long"])
+def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
+    """The tcgen05 int8 contraction (count_tc.cuh) against the popcount kernel and the oracle's
+    string scan: rectangles that are not multiples of the 128 x 128 tile, offsets into the sets,
+    two sets of different width, leading / trailing / internal gaps (the trim correction in the
+    epilogue), missing symbols, lower case, rows far longer than a barcode."""
+    from taxi2_b200.engine import pack_strings
+
+    rng = np.random.default_rng({"ragged": 1, "prealigned": 2, "two_sets": 3, "long": 4}[case])
+    if case == "ragged":
+        xs = _junk_rows(rng, 300, 0, 400)
+        ys = None
+    elif case == "prealigned":
+        base = _junk_rows(rng, 1, 618, 618, b"ACGT")[0]
+        xs = []
+        for _ in range(450):
+            s = np.frombuffer(base.encode(), dtype=np.uint8).copy()
+            hit = rng.random(618) < 0.12
+            s[hit] = np.frombuffer(b"ACGT-N", dtype=np.uint8)[rng.choice(6, int(hit.sum()), p=[.22, .22, .22, .22, .09, .03])]
+            lead, trail = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+            s[:lead] = ord("-"); s[618 - trail:] = ord("-")
+            xs.append(s.tobytes().decode())
+        ys = None
+    elif case == "two_sets":
+        xs = _junk_rows(rng, 200, 100, 300, b"ACGT-N", [.23, .23, .23, .23, .06, .02])
+        ys = _junk_rows(rng, 333, 250, 700, b"ACGT-N", [.23, .23, .23, .23, .06, .02])
+    else:
+        xs = _junk_rows(rng, 140, 5000, 5200, b"ACGT-N", [.24, .24, .24, .24, .03, .01])
+        ys = None
+    engine.load(xs, 0)
+    if ys is not None:
+        engine.load(ys, 1)
+    cols = ys if ys is not None else xs
+    nx, ny = len(xs), len(cols)
+    results = {}
+    for kernel in (1, 2):
+        engine.set_option("count_kernel", kernel)
+        try:
+            full = engine.count_rect(0, nx, 0, ny)
+            assert engine.last_kernel == (8 if kernel == 1 else 9)
+            part = engine.count_rect(37, nx - 50, 11, ny - 29)
+        finally:
+            engine.set_option("count_kernel", 0)
+        results[kernel] = full
+        assert np.array_equal(part["counts"], full["counts"][37:nx - 13, 11:ny - 18])
+        assert np.array_equal(part["metrics"], full["metrics"][37:nx - 13, 11:ny - 18], equal_nan=True)
+    assert np.array_equal(results[1]["counts"], results[2]["counts"])
+    assert np.array_equal(results[1]["metrics"], results[2]["metrics"], equal_nan=True)
+    data, off = pack_strings(xs + (ys or []))
+    px = rng.integers(0, nx, 3000).astype(np.int32)
+    py = rng.integers(0, ny, 3000).astype(np.int32)
+    want = oracle.count_pairs(data, off, px, py + (nx if ys is not None else 0))
+    assert np.array_equal(results[2]["counts"][px, py], want["counts"])
+    assert_metrics_close(results[2]["metrics"][px, py], want["metrics"])
