@@ -30,9 +30,12 @@
 // subtracted in the epilogue exactly as in the popcount kernel (gaps_outside_trim on the planes),
 // and the fp64 metrics are computed there too, so the kernel writes the same 16 B + 32 B per pair.
 //
-// One CTA per tile, one CTA per SM (the four accumulators take all 512 TMEM columns): warp 0 feeds
-// TMA, warp 1 issues the MMAs, 16 epilogue warps (4 per TMEM lane quarter, 32 columns each) do
-// trim, metrics and stores -- the epilogue, not the contraction, is what bounds the kernel.
+// One CTA of 32 warps per tile, one CTA per SM (the four accumulators take all 512 TMEM columns).
+// The y tile is the A operand, so a TMEM lane -- an epilogue thread -- is a y column and the 32
+// threads of a warp write 32 consecutive pairs of one x row: the same coalesced 16 B + 32 B per pair
+// as the popcount kernel.  Lane 0 of warp 0 feeds TMA, lane 0 of warp 1 issues the MMAs, then all
+// 32 warps (4 TMEM lane quarters x 8 groups of 16 x rows) do trim, metrics and stores -- the
+// epilogue, not the contraction, is what bounds the kernel.
 #pragma once
 #include <cuda.h>
 
@@ -43,8 +46,7 @@ namespace taxi {
 constexpr int TC_TILE = 128;              // pairs per tile side; also bytes of K per pipeline stage
 constexpr int TC_UMMA_K = 32;             // bytes of K per tcgen05.mma (8-bit operands)
 constexpr int TC_STAGES = 5;
-constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 1024;
 constexpr int TC_ROW_SEGMENTS = 8;        // row length in units of Lp
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * 2 * TC_TILE * TC_TILE + 1024;
 
@@ -181,75 +183,76 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     auto segment = [&](int kb, int& acc, int& kx, int& ky) {
         const int unit = kb / blocks_per_L, within = (kb % blocks_per_L) * TC_TILE;   // unit: 0 R, 1 u1, 2-3 u0/u0u1, 4-5 gap
         acc = unit == 0 ? 0 : unit == 1 ? 1 : unit < 4 ? 2 : 3;
-        const int seg_x = unit < 4 ? unit : unit;              // x rows: segments 0..5 in order
-        const int seg_y = unit < 4 ? unit : unit + 2;          // y rows: the gap segment of the y role is 6..7
-        kx = seg_x * args.LpX + within;
-        ky = seg_y * args.LpY + within;
+        // the two-unit segments are interleaved byte pairs: 2 Lp consecutive bytes of the pair's common columns,
+        // starting at the segment's base in each row (bases depend on the row's own Lp)
+        const int first = acc == 2 ? 2 : acc == 3 ? 4 : unit;               // first unit of this accumulator
+        const int into = (unit - first) * Lp + within;                      // byte offset inside the segment
+        kx = first * args.LpX + into;
+        ky = (acc == 3 ? 6 : first) * args.LpY + into;                      // the gap segment of the y role
     };
 
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % TC_STAGES;
-                int acc, kx, ky;
-                segment(kb, acc, kx, ky);
-                mbar_wait(empty + s, ((kb / TC_STAGES) & 1) ^ 1);
-                mbar_expect_tx(full + s, 2 * STAGE_BYTES);
-                tma_load_2d(sX + s * STAGE_BYTES, &map_x, full + s, kx, a.x0 + xt);
-                tma_load_2d(sY + s * STAGE_BYTES, &map_y, full + s, ky, a.y0 + yt);
-            }
+    if (warp == 0 && lane == 0) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int s = kb % TC_STAGES;
+            int acc, kx, ky;
+            segment(kb, acc, kx, ky);
+            mbar_wait(empty + s, ((kb / TC_STAGES) & 1) ^ 1);
+            mbar_expect_tx(full + s, 2 * STAGE_BYTES);
+            tma_load_2d(sX + s * STAGE_BYTES, &map_x, full + s, kx, a.x0 + xt);
+            tma_load_2d(sY + s * STAGE_BYTES, &map_y, full + s, ky, a.y0 + yt);
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // S32 accumulators, signed 8-bit A and B, both K-major, N = 128, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
-            int prev_acc = -1;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % TC_STAGES;
-                int acc, kx, ky;
-                segment(kb, acc, kx, ky);
-                mbar_wait(full + s, (kb / TC_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (warp == 1 && lane == 0) {
+        // S32 accumulators, signed 8-bit A and B, both K-major, N = 128, M = 128; A = the y tile (TMEM lanes), B = the x tile
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+        int prev_acc = -1;
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int s = kb % TC_STAGES;
+            int acc, kx, ky;
+            segment(kb, acc, kx, ky);
+            mbar_wait(full + s, (kb / TC_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < TC_TILE / TC_UMMA_K; ++k)
-                    umma_i8(tmem + (uint32_t)(acc * TC_TILE), umma_desc(sX + s * STAGE_BYTES, k * TC_UMMA_K),
-                            umma_desc(sY + s * STAGE_BYTES, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
-                prev_acc = acc;
-                umma_commit(empty + s);
-            }
-            umma_commit(accum_full);
+            for (int k = 0; k < TC_TILE / TC_UMMA_K; ++k)
+                umma_i8(tmem + (uint32_t)(acc * TC_TILE), umma_desc(sY + s * STAGE_BYTES, k * TC_UMMA_K),
+                        umma_desc(sX + s * STAGE_BYTES, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
+            prev_acc = acc;
+            umma_commit(empty + s);
         }
-    } else {
-        mbar_wait(accum_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int e = warp - 2;
-        const int q = warp & 3;                          // this warp reaches TMEM lanes [32 q, 32 q + 32)
-        const int cg = e >> 2;                           // its 32 columns of the tile
-        const int xr = xt + q * 32 + lane;               // row inside the rectangle
-        const bool row_ok = xr < a.nx;
-        const int xs = a.x0 + min(xr, a.nx - 1);
-        const int2 sx = __ldg(a.x.span + xs);
+        umma_commit(accum_full);
+    }
+    __syncwarp();
+
+    // ---- epilogue: every warp ------------------------------------------------------------------
+    mbar_wait(accum_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const int q = warp & 3;                          // this warp reaches TMEM lanes [32 q, 32 q + 32): its 32 y columns
+        const int cg = warp >> 2;                        // its 16 x rows of the tile
+        const int yc = yt + q * 32 + lane;               // column inside the rectangle
+        const bool col_ok = yc < a.ny;
+        const int ys = a.y0 + min(yc, a.ny - 1);
+        const int2 sy = __ldg(a.y.span + ys);
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            const int c0 = cg * 32 + ch * 8;
+        for (int ch = 0; ch < 2; ++ch) {
+            const int r0 = cg * 16 + ch * 8;
             int A0[8], A1[8], A2[8], A3[8];
-            tmem_ld8(lane_addr + (uint32_t)(0 * TC_TILE + c0), A0);
-            tmem_ld8(lane_addr + (uint32_t)(1 * TC_TILE + c0), A1);
-            tmem_ld8(lane_addr + (uint32_t)(2 * TC_TILE + c0), A2);
-            tmem_ld8(lane_addr + (uint32_t)(3 * TC_TILE + c0), A3);
+            tmem_ld8(lane_addr + (uint32_t)(0 * TC_TILE + r0), A0);
+            tmem_ld8(lane_addr + (uint32_t)(1 * TC_TILE + r0), A1);
+            tmem_ld8(lane_addr + (uint32_t)(2 * TC_TILE + r0), A2);
+            tmem_ld8(lane_addr + (uint32_t)(3 * TC_TILE + r0), A3);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int yc = yt + c0 + k;
-                if (row_ok && yc < a.ny) {
+                const int xr = xt + r0 + k;              // row inside the rectangle (the same for the whole warp)
+                if (xr < a.nx && col_ok) {
                     const int n = A0[k];
                     const int ts = (n + A1[k] - A2[k]) >> 2, tv = (n - A1[k]) >> 1;
                     int gap = A3[k];
-                    const int ys = a.y0 + yc;
+                    const int xs = a.x0 + xr;
                     if (n > 0 && gap > 0)
                         gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xs); }, [&](int w) { return a.y.at(w, ys); },
-                                                 sx, __ldg(a.y.span + ys));
+                                                 __ldg(a.x.span + xs), sy);
                     store_pair(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0);
                 }
             }
