@@ -40,7 +40,9 @@ n = len(off) - 1
 eng.load((data, off), 0)
 c = torch.empty((n * n, 4), dtype=torch.int32, device="cuda")
 m = torch.empty((n * n, 4), dtype=torch.float64, device="cuda")
-for _ in range(2):
+for kernel in (1, 2, 2):   # popcount kernel, then the tensor-core kernel twice (the first launch builds its operands)
+    eng.set_option("count_kernel", kernel)
+    before = eng.stats()["kernel_ms"]
     eng.count_rect_device(0, n, 0, n, c.data_ptr(), m.data_ptr())
     eng.sync()
-    print("count_rect", n, "x", n, "ms", round(eng.stats()["kernel_ms"], 3))
+    print("count", {1: "popcount", 2: "tensor cores"}[kernel], n, "x", n, "ms", round(eng.stats()["kernel_ms"] - before, 3))
