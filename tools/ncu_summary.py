@@ -14,7 +14,8 @@ KEEP = [
     "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
     "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
     "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
@@ -31,7 +32,8 @@ for r in rows[start + 2:]:
         continue
     rec = {}
     for name, unit, val in zip(header, units, r):
-        if name in KEEP:
+        if name in KEEP or name.split(".", 2)[-1] in KEEP:
+            name = name.split(".", 2)[-1] if name.split(".", 2)[-1] in KEEP else name
             rec[name] = [val, unit]
     out.append(rec)
 json.dump(out, sys.stdout, indent=1)
