@@ -587,7 +587,7 @@ def run_config(args) -> None:
             return multi.count_matrix(want=("counts", "metrics"), out=out)
 
         value_pairs, cells = pairs, 0
-        kernel = "count_rect_kernel"
+        kernel = "count_tc_kernel (tcgen05 int8 contraction + fused trim/metric epilogue)"
         h2d, d2h = data.nbytes + off.nbytes, counts.nbytes + metrics.nbytes
         cpu_run = lambda: cpu_count_throughput(data, off, args.cpu_seconds)   # noqa: E731
         cpu_sample = "random ordered pairs of the C2 rows"
@@ -696,6 +696,8 @@ def run_config(args) -> None:
 
     value = value_pairs * args.steps / dt
     if cfg == "C2":
+        if multi.engines[0].last_kernel == 8:
+            kernel = "count_rect_kernel (popcount)"
         bytes_per_pair = 48.0
         launch_s = kernel_ms / 1e3 / max(launches, 1)
         pairs_per_launch = pairs * args.steps / max(launches, 1)

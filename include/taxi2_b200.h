@@ -114,8 +114,12 @@ int taxi_align_strings_metrics(taxi_ctx* ctx, const int32_t* px, const int32_t* 
 
 /*
  * Alignment-free mode (params.pairs.align = False, versus_all.py:522-530): per-pair counts and
- * metrics straight from the loaded (pre-aligned) sequences, bit-sliced XOR/popcount.
- * Replaces calc.seq_distances_* applied to the raw strings (distances.py:323-347).
+ * metrics straight from the loaded (pre-aligned) sequences.  Replaces calc.seq_distances_* applied
+ * to the raw strings (distances.py:323-347).  Rectangles of a few hundred thousand pairs and more
+ * run as an int8 contraction on the tensor cores (tcgen05 + TMA + TMEM, count_tc.cuh) with the
+ * trim rule and the fp64 metrics fused into its epilogue; pair lists, small rectangles and rows
+ * too long for its operand layout run on the bit-sliced XOR/popcount kernel (count_planes.cuh).
+ * Same results either way (option "count_kernel").
  */
 int taxi_count_rect(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
                     int32_t* out_counts, double* out_metrics);
@@ -203,7 +207,9 @@ void taxi_host_free(void* p);
  * positions are the same either way).  taxi_last_kernel() reports which kernel the last alignment
  * call used: 32 = gotoh_warp (int32), 16 = gotoh_pair16 top-aligned, 17 = gotoh_pair16
  * bottom-aligned, 18 = gotoh_pair16 bottom-aligned in several stripes (x longer than 1023),
- * 48 = a rectangle whose rows were grouped by length into several launches.
+ * 48 = a rectangle whose rows were grouped by length into several launches; after an alignment-free
+ * call: 8 = popcount kernel, 9 = tensor-core kernel.  "count_kernel" = 1 / 2 forces the popcount /
+ * the tensor-core kernel for alignment-free rectangles (0 = whichever fits; tests compare the two).
  */
 int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
 int taxi_last_kernel(taxi_ctx* ctx);
