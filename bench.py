@@ -705,7 +705,9 @@ def run_config(args) -> None:
         mhz = clk.get("sm_mhz") or 1965.0
         W = (618 + 31) // 32
         roof = dict(bound="hbm", kernel=kernel, achieved=pairs_per_launch * bytes_per_pair / launch_s / 1e9, peak=hbm, unit="GB/s",
-                    frac=pairs_per_launch * bytes_per_pair / launch_s / 1e9 / hbm, traffic=(ncu_traffic(kernel) or {}).get("bytes_per_pair", None),
+                    frac=pairs_per_launch * bytes_per_pair / launch_s / 1e9 / hbm,
+                    traffic=(ncu_traffic(kernel) or {}).get("bytes_per_pair", 0) * pairs_per_launch or None,
+                    traffic_source=(ncu_traffic(kernel) or {}).get("source"),
                     how=f"{bytes_per_pair:.0f} algorithmic bytes/pair (16 B counts + 32 B metrics written once; the {n * W * 16 / 1e6:.1f} MB of bit planes are "
                         f"re-read from L2) x {pairs_per_launch:.3e} pairs/launch / {launch_s * 1e3:.3f} ms per launch (CUDA events); peak = {hbm_how}",
                     int32=dict(ops_per_pair=12 * W, achieved=pairs_per_launch * 12 * W / launch_s / 1e9, peak=lanes * sms * mhz * 1e6 / 1e9, unit="Gop/s",
