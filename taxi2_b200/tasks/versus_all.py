@@ -330,6 +330,7 @@ class NativeBlockWriter:
         self.summary_path = task.paths.summary
         self.agg = {"genera": agg_genera, "species": agg_species}
         self.header_done = False
+        self.pool = None
         # the Python handlers stay open (they create / truncate the files) but never receive a row;
         # they are closed before the first native append so the two never interleave
         self.python_handles = [h for h in [linear_file, *matrix_files] if h is not None]
@@ -384,27 +385,41 @@ class NativeBlockWriter:
             self.header_done = True
         fw = fastwrite
         n, m = self.n, block.metrics
+        # every file (and every subset aggregate) is independent of the others: the native calls run
+        # side by side on a few host threads (ctypes drops the GIL), each appending to its own file
+        jobs = []
         if self.linear_path is not None:
-            fw.format_pairs(self.linear_path, [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES], [self.t_rec], [self.t_rec], block.x0, block.nx, n,
-                            m, undefined, self.columns, self.scale, self.fmtc, self.missing)
+            jobs.append(lambda: fw.format_pairs(self.linear_path, [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES], [self.t_rec], [self.t_rec],
+                                                block.x0, block.nx, n, m, undefined, self.columns, self.scale, self.fmtc, self.missing))
         for path, col in zip(self.matrix_paths, self.columns):
-            fw.format_matrix(path, self.t_id, block.x0, block.nx, n, m, undefined, col, self.scale, self.fmtc, self.missing)
+            jobs.append(lambda path=path, col=col: fw.format_matrix(path, self.t_id, block.x0, block.nx, n, m, undefined, col, self.scale,
+                                                                    self.fmtc, self.missing))
         seg = [fw.SEG_X[0], fw.SEG_Y[0], fw.SEG_SCORES]
         if self.has_extras:
             seg += [fw.SEG_X[1], fw.SEG_Y[1]]
         seg += [fw.SEG_X[2], fw.SEG_Y[2], fw.SEG_COMPARISON]
         g, s = self.ids["genera"], self.ids["species"]
-        fw.format_pairs(self.summary_path, seg, [self.t_id, self.t_extras, self.t_taxon], [self.t_id, self.t_extras, self.t_taxon],
-                        block.x0, block.nx, n, m, undefined, self.columns, self.scale, self.fmtc, self.missing,
-                        xgenus=g[0] if g else None, xspecies=s[0] if s else None, ygenus=g[0] if g else None, yspecies=s[0] if s else None)
+        jobs.append(lambda: fw.format_pairs(self.summary_path, seg, [self.t_id, self.t_extras, self.t_taxon],
+                                            [self.t_id, self.t_extras, self.t_taxon], block.x0, block.nx, n, m, undefined, self.columns,
+                                            self.scale, self.fmtc, self.missing, xgenus=g[0] if g else None, xspecies=s[0] if s else None,
+                                            ygenus=g[0] if g else None, yspecies=s[0] if s else None))
         for name in ("genera", "species"):
             if self.ids[name] is None:
                 continue
             agg_ids = self.ids[name][1]
             for state, col in zip(self.states[name], self.columns):
-                state.add_block(m, undefined, block.x0, block.nx, n, col, self.scale, agg_ids, agg_ids)
+                jobs.append(lambda state=state, col=col, agg_ids=agg_ids: state.add_block(m, undefined, block.x0, block.nx, n, col,
+                                                                                         self.scale, agg_ids, agg_ids))
+        if self.pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(max_workers=6, thread_name_prefix="taxi-writer")
+        for future in [self.pool.submit(job) for job in jobs]:
+            future.result()
 
     def finish(self) -> None:
+        if self.pool is not None:
+            self.pool.shutdown()
+            self.pool = None
         if not self.header_done:   # no sequences at all: the handlers produced the (empty) files
             for h in self.python_handles:
                 h.close()
