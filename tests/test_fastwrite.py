@@ -172,3 +172,30 @@ def test_aligned_pair_records_match_the_python_handler(tmp_path):
         fw.format_aligned_pairs(out, k == 0, fw.StringTable([idx]), fw.StringTable([idy]), 0, 1, 1, np.frombuffer(ax, dtype=np.uint8).copy(),
                                 np.frombuffer(ay, dtype=np.uint8).copy(), np.zeros(1, dtype=np.int64), np.array([0, 4], dtype=np.int64))
     assert out.read_bytes() == (Path(__file__).parent / "golden" / "pairs_simple.formatted").read_bytes()
+
+
+@pytest.mark.parametrize("spec", ["{:.4f}", "{:.0f}", "{:.2f}", "{:.9f}", "{:f}"])
+def test_fixed_point_fast_path_equals_python_format(tmp_path, spec):
+    """The integer-arithmetic formatter behind "%.Nf" (host_format.cpp: append_fixed) against
+    Python's own format over magnitudes from subnormal to 1e15, exact decimal ties (0.125, 2.5,
+    0.00005 ...), values a hair on either side of a tie, negative values and negative zero."""
+    from taxi2_b200 import fastwrite
+
+    rng = np.random.default_rng(len(spec))
+    vals = [0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 0.375, 0.00005, 0.00015, 0.99995, 0.999949999999, 1e-300, 5e-324, 123456789.987654321,
+            9.999999999e14, 0.1, 0.2, 0.3, 1 / 3, 2 / 3, 0.07, 0.0625, 0.03125, 1e15 + 0.5, 4503599627370497.0, 1e22]
+    for k in range(1, 40):
+        base = k / 20000.0            # multiples of 0.00005: ties of "{:.4f}" when exactly representable
+        vals += [base, np.nextafter(base, 1.0), np.nextafter(base, 0.0)]
+    vals += list(rng.random(20000)) + list(rng.random(5000) * 10.0 ** rng.integers(-12, 14, 5000)) + list(-rng.random(2000))
+    vals = np.array(vals, dtype=np.float64)
+    n = len(vals)
+    m = np.zeros((1, n, 4))
+    m[0, :, 2] = vals
+    ids = fastwrite.StringTable(["row"])
+    path = tmp_path / "m.tsv"
+    path.write_bytes(b"")
+    fastwrite.format_matrix(path, ids, 0, 1, n, m, None, 2, 1.0, fastwrite.printf_format(spec), "NA")
+    got = path.read_text().rstrip("\n").split("\t")[1:]
+    want = [spec.format(v) for v in vals]
+    assert got == want
