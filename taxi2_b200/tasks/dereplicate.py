@@ -56,7 +56,8 @@ def output_handler(fmt: FileFormat, path: Path):
 
 
 class Dereplicate:
-    rows_per_block = None   # rows per device block (None: about 2M pairs per block)
+    rows_per_block = None   # rows per device block (None: about 1M pairs in a block's first chunk of columns)
+    first_columns = None    # columns a block is aligned against before any of its rows asks for more (None: 4096)
 
     def __init__(self):
         self.work_dir: Path = None
@@ -107,10 +108,14 @@ class Dereplicate:
           after which the reference's pair filter drops the rest of the row.
 
         Python objects are only built for pairs that are written (aligned pairs / distance files
-        enabled) and for the summary lines.  When more than half of the loaded sequences have been
-        excluded the survivors are re-loaded, so the device stops computing dead columns.  With
-        several GPUs (task.devices) row blocks are computed ahead on all of them; the walk stays
-        sequential.  Inputs with repeated ids keep the per-pair path (the exclusion set is keyed by
+        enabled) and for the summary lines.  Distances are computed LAZILY along the columns: a
+        block of rows is aligned against a first chunk of columns, and only when a row survives
+        everything computed so far is the block extended (four times wider each time) -- most rows
+        are excluded by the first longer similar sequence within a few thousand columns, and the
+        reference would not have aligned the rest of their rows either.  When more than half of the
+        loaded sequences have been excluded the survivors are re-loaded, so the device stops
+        computing dead columns.  With several GPUs (task.devices) the rows of a chunk are split over
+        them; the walk stays sequential.  Inputs with repeated ids keep the per-pair path (the exclusion set is keyed by
         id, and the reference's groupby merges neighbouring rows of equal id)."""
         ids = [s.id for s in self.input]
         if len(set(ids)) != len(ids):
@@ -176,41 +181,85 @@ class Dereplicate:
                     side.load([work[k].seq for k in loaded], 0)
                 m = len(loaded)
                 len_loaded = raw_len[loaded]
-                rows_per_tile = self.rows_per_block or max(1, min(256, (1 << 21) // max(m, 1)))
-                tiles = multi.row_tiles(rows_per_tile, 1, (first_pos, m))
+                first_chunk = min(m, self.first_columns or 4096)
+                rows_per_block = self.rows_per_block or max(8, min(256, (1 << 20) // max(first_chunk, 1)))
 
-                def compute(eng, tile, slot):
-                    call = eng.align_rect if p.pairs.align else eng.count_rect
-                    return call(tile.x0, tile.nx, 0, m, want=("metrics",))["metrics"][..., col]
+                def compute_rect(r0, r1, c0, c1):
+                    """Main-metric distances of rows [r0, r1) x columns [c0, c1) of the loaded set; rows are
+                    split over the GPUs when the rectangle is large enough to keep several busy."""
+                    ngpu = len(multi.engines)
+                    parts = ngpu if (r1 - r0) >= ngpu and (r1 - r0) * (c1 - c0) >= ngpu * (1 << 17) else 1
+                    cuts = [r0 + (r1 - r0) * k // parts for k in range(parts + 1)]
+                    out = [None] * parts
 
-                blocks = multi.run_tiles(tiles, compute, depth=2, ordered=True)
-                try:
-                    for tile, values in blocks:
-                        self.stats["pairs_computed"] += tile.nx * m
-                        for bx in range(tile.nx):
-                            pos = tile.x0 + bx
-                            i = int(loaded[pos])
-                            pointer = i + 1
-                            if not alive[i]:
-                                continue
-                            live = alive[loaded]
-                            live[pos] = False                      # x.id != y.id
-                            idx = np.nonzero(live)[0]
+                    def one(k):
+                        eng = multi.engines[k]
+                        call = eng.align_rect if p.pairs.align else eng.count_rect
+                        out[k] = call(cuts[k], cuts[k + 1] - cuts[k], c0, c1 - c0, want=("metrics",))["metrics"][..., col]
+
+                    if parts == 1:
+                        one(0)
+                    else:
+                        import threading
+                        threads = [threading.Thread(target=one, args=(k,), daemon=True) for k in range(parts)]
+                        for t in threads:
+                            t.start()
+                        for t in threads:
+                            t.join()
+                        if any(o is None for o in out):
+                            raise RuntimeError("a device failed while computing a block of distances")
+                    self.stats["pairs_computed"] += (r1 - r0) * (c1 - c0)
+                    return np.concatenate(out, axis=0) if parts > 1 else out[0]
+
+                pos = first_pos
+                reload = False
+                while pos < m and not reload:
+                    block_end = min(m, pos + rows_per_block)
+                    values = np.empty((block_end - pos, m), dtype=np.float64)
+                    have = 0          # columns [0, have) are computed for every row of the block not walked yet
+                    for r in range(pos, block_end):
+                        i = int(loaded[r])
+                        pointer = i + 1
+                        if not alive[i]:
+                            continue
+                        x = data[i]
+                        first_d, have_first = None, False
+                        c0 = 0
+                        row_over = False
+                        while c0 < m and not row_over:
+                            if c0 >= have:
+                                # Most rows die within their first few thousand columns (the first longer
+                                # similar sequence excludes them), so a block is aligned against a first
+                                # chunk of columns only and extended -- four times wider each time, for the
+                                # rows still to be walked -- when a row survives what has been computed.
+                                nxt = min(m, max(first_chunk, 4 * have))
+                                values[r - pos:, have:nxt] = compute_rect(r, block_end, have, nxt)
+                                have = nxt
+                            c1 = have
+                            live = alive[loaded[c0:c1]]
+                            if c0 <= r < c1:
+                                live[r - c0] = False                   # x.id != y.id
+                            idx = np.nonzero(live)[0] + c0
+                            c0 = c1
                             if idx.size == 0:
                                 continue
-                            d = values[bx, idx] * scale
+                            d = values[r - pos, idx] * scale
                             with np.errstate(invalid="ignore"):
                                 similar = np.isfinite(d) & (d <= similarity)
                             longer = similar & (len_loaded[idx] > raw_len[i])
-                            stop = int(np.argmax(longer)) if longer.any() else idx.size - 1
+                            if longer.any():
+                                stop = int(np.argmax(longer))
+                                row_over = True                        # x is excluded there: the rest of the row is never pulled
+                            else:
+                                stop = idx.size - 1
                             visited = idx[: stop + 1]
                             dv, sv = d[: stop + 1], similar[: stop + 1]
-                            x = data[i]
-                            first_d = float(dv[0]) if np.isfinite(dv[0]) else None
+                            if not have_first:
+                                first_d, have_first = (float(dv[0]) if np.isfinite(dv[0]) else None), True
                             if writes_pairs:
                                 strings = None
-                                if pairs_file is not None:   # one launch for the row's visited columns
-                                    ax, ay, _ = side.align_strings(np.full(len(visited), pos, dtype=np.int32), visited.astype(np.int32))
+                                if pairs_file is not None:   # one launch for the visited columns of this stretch of the row
+                                    ax, ay, _ = side.align_strings(np.full(len(visited), r, dtype=np.int32), visited.astype(np.int32))
                                     strings = (ax, ay)
                                 for q, vpos in enumerate(visited):
                                     j = int(loaded[vpos])
@@ -236,16 +285,14 @@ class Dereplicate:
                                 summary.write((x.id, str(int(raw_len[i])), inc[0], str(inc[1]), text(inc[2]), exc[0], str(exc[1]), text(exc[2])))
                             done += len(visited)
                             self.stats["pairs_visited"] += len(visited)
-                            now = perf_counter()
-                            if now - last >= self.progress_interval:
-                                self.progress_handler("distance.x.id", done, total - len(self.excluded) * n)
-                                last = now
-                        # the device keeps computing the columns that died since the load: start over
-                        # with the survivors once that is more than half of the loaded set
-                        if int(alive[loaded].sum()) * 2 < m and pointer < n:
-                            break
-                finally:
-                    blocks.close()
+                        now = perf_counter()
+                        if now - last >= self.progress_interval:
+                            self.progress_handler("distance.x.id", done, total - len(self.excluded) * n)
+                            last = now
+                    pos = block_end
+                    # the device keeps computing the columns that died since the load: start over
+                    # with the survivors once that is more than half of the loaded set
+                    reload = int(alive[loaded].sum()) * 2 < m and pointer < n
             self.progress_handler("Finalizing...", total, total)
         finally:
             for w in writers:

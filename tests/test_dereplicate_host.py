@@ -47,9 +47,10 @@ def cpu_engines(monkeypatch):
     return multi
 
 
-@pytest.mark.parametrize("seed,align,write,multiply,rows", [(1, True, True, False, 3), (2, True, False, True, 5), (3, False, False, False, 2),
-                                                             (4, True, False, False, None), (5, False, True, False, 1)])
-def test_block_replay_matches_the_per_pair_pipeline(tmp_path, cpu_engines, seed, align, write, multiply, rows):
+@pytest.mark.parametrize("seed,align,write,multiply,rows,first", [
+    (1, True, True, False, 3, 4), (2, True, False, True, 5, 2), (3, False, False, False, 2, 7), (4, True, False, False, None, None),
+    (5, False, True, False, 1, 1), (6, True, True, False, 4, 5), (7, False, False, True, 6, 3)])
+def test_block_replay_matches_the_per_pair_pipeline(tmp_path, cpu_engines, seed, align, write, multiply, rows, first):
     rng = np.random.default_rng(seed)
     records = clusters(rng, nclusters=5, per=6, length=60)
     records.append(Sequence("tiny", "acg", {"organism": "x y"}))                # dropped by the length threshold
@@ -59,6 +60,7 @@ def test_block_replay_matches_the_per_pair_pipeline(tmp_path, cpu_engines, seed,
     task.input = Sequences(records)
     task.output_format = FileFormat.Tabfile
     task.rows_per_block = rows
+    task.first_columns = first     # columns aligned before a row asks for more: small values force the lazy extension
     task.params.pairs.align, task.params.pairs.write = align, write
     task.params.distances.write_linear = task.params.distances.write_matricial = write or seed == 2
     task.params.format.percentage_multiply = multiply
@@ -78,6 +80,8 @@ def test_block_replay_matches_the_per_pair_pipeline(tmp_path, cpu_engines, seed,
     # the survivors were re-loaded at least once, and far fewer pairs were visited than n^2
     assert task.stats["reloads"] >= (2 if rows else 1)
     assert task.stats["pairs_visited"] < len(records) ** 2 / 2
+    if first:   # the lazy evaluation computed less than the full rows of every walked block
+        assert task.stats["pairs_computed"] < task.stats["reloads"] * len(records) ** 2
 
 
 def test_repeated_ids_take_the_per_pair_path(tmp_path, cpu_engines):
@@ -94,3 +98,22 @@ def test_repeated_ids_take_the_per_pair_path(tmp_path, cpu_engines):
     assert task.excluded == excluded
     got, want = tree(task.work_dir), tree(tmp_path / "want")
     assert got == want
+
+
+def test_block_replay_on_a_larger_set_with_lazy_columns(tmp_path, cpu_engines):
+    rng = np.random.default_rng(42)
+    records = clusters(rng, nclusters=8, per=12, length=50, sub=0.03)
+    task = Dereplicate()
+    task.work_dir = tmp_path / "got"
+    task.progress_handler = lambda *a: None
+    task.input = Sequences(records)
+    task.output_format = FileFormat.Fasta
+    task.rows_per_block = 5
+    task.first_columns = 6
+    task.params.pairs.write = False
+    task.start()
+    excluded = ref_pipeline.dereplicate(records, tmp_path / "want", fasta=True)
+    (tmp_path / "want" / "aligned_pairs.txt").unlink()
+    assert task.excluded == excluded
+    assert tree(task.work_dir) == tree(tmp_path / "want")
+    assert task.stats["pairs_computed"] < 0.8 * len(records) ** 2
