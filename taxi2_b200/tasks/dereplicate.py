@@ -57,7 +57,7 @@ def output_handler(fmt: FileFormat, path: Path):
 
 class Dereplicate:
     rows_per_block = None   # rows per device block (None: about 1M pairs in a block's first chunk of columns)
-    first_columns = None    # columns a block is aligned against before any of its rows asks for more (None: 4096)
+    first_columns = None    # columns past its own end a block is aligned against before a row asks for more (None: 2048)
 
     def __init__(self):
         self.work_dir: Path = None
@@ -112,7 +112,7 @@ class Dereplicate:
         block of rows is aligned against a first chunk of columns, and only when a row survives
         everything computed so far is the block extended (four times wider each time) -- most rows
         are excluded by the first longer similar sequence within a few thousand columns, and the
-        reference would not have aligned the rest of their rows either.  When more than half of the
+        reference would not have aligned the rest of their rows either.  When 30 % of the
         loaded sequences have been excluded the survivors are re-loaded, so the device stops
         computing dead columns.  With several GPUs (task.devices) the rows of a chunk are split over
         them; the walk stays sequential.  Inputs with repeated ids keep the per-pair path (the exclusion set is keyed by
@@ -181,7 +181,7 @@ class Dereplicate:
                     side.load([work[k].seq for k in loaded], 0)
                 m = len(loaded)
                 len_loaded = raw_len[loaded]
-                first_chunk = min(m, self.first_columns or 4096)
+                first_chunk = min(m, self.first_columns or 2048)
                 rows_per_block = self.rows_per_block or max(8, min(256, (1 << 20) // max(first_chunk, 1)))
 
                 def compute_rect(r0, r1, c0, c1):
@@ -216,7 +216,13 @@ class Dereplicate:
                 while pos < m and not reload:
                     block_end = min(m, pos + rows_per_block)
                     values = np.empty((block_end - pos, m), dtype=np.float64)
-                    have = 0          # columns [0, have) are computed for every row of the block not walked yet
+                    # A row is excluded by the first LONGER similar sequence it meets.  The columns before
+                    # the block are rows already walked (after a reload: the survivors so far, few and
+                    # rarely similar to anything left); the likely partners are the next few thousand.
+                    # So a block is aligned against the columns up to `first_chunk` past its own end, and
+                    # a row that survives those is extended on its own, eight times wider each time.
+                    first_end = min(m, block_end + first_chunk)
+                    values[:, :first_end] = compute_rect(pos, block_end, 0, first_end)
                     for r in range(pos, block_end):
                         i = int(loaded[r])
                         pointer = i + 1
@@ -225,15 +231,12 @@ class Dereplicate:
                         x = data[i]
                         first_d, have_first = None, False
                         c0 = 0
+                        have = first_end      # columns [0, have) of this row are computed
                         row_over = False
                         while c0 < m and not row_over:
                             if c0 >= have:
-                                # Most rows die within their first few thousand columns (the first longer
-                                # similar sequence excludes them), so a block is aligned against a first
-                                # chunk of columns only and extended -- four times wider each time, for the
-                                # rows still to be walked -- when a row survives what has been computed.
-                                nxt = min(m, max(first_chunk, 4 * have))
-                                values[r - pos:, have:nxt] = compute_rect(r, block_end, have, nxt)
+                                nxt = min(m, have + 8 * (have - pos))
+                                values[r - pos, have:nxt] = compute_rect(r, r + 1, have, nxt)[0]
                                 have = nxt
                             c1 = have
                             live = alive[loaded[c0:c1]]
@@ -291,8 +294,8 @@ class Dereplicate:
                             last = now
                     pos = block_end
                     # the device keeps computing the columns that died since the load: start over
-                    # with the survivors once that is more than half of the loaded set
-                    reload = int(alive[loaded].sum()) * 2 < m and pointer < n
+                    # with the survivors once 30 % of the loaded set is gone
+                    reload = int(alive[loaded].sum()) * 10 < 7 * m and pointer < n
             self.progress_handler("Finalizing...", total, total)
         finally:
             for w in writers:
