@@ -109,10 +109,10 @@ class Dereplicate:
 
         Python objects are only built for pairs that are written (aligned pairs / distance files
         enabled) and for the summary lines.  Distances are computed LAZILY along the columns: a
-        block of rows is aligned against a first chunk of columns, and only when a row survives
-        everything computed so far is the block extended (four times wider each time) -- most rows
-        are excluded by the first longer similar sequence within a few thousand columns, and the
-        reference would not have aligned the rest of their rows either.  When 30 % of the
+        block of rows is aligned against the columns up to a couple of thousand past its own end,
+        and a row that survives all of those is extended on its own (eight times wider each time)
+        -- most rows are excluded by the first longer similar sequence among the next few thousand,
+        and the reference would not have aligned the rest of their rows either.  When 30 % of the
         loaded sequences have been excluded the survivors are re-loaded, so the device stops
         computing dead columns.  With several GPUs (task.devices) the rows of a chunk are split over
         them; the walk stays sequential.  Inputs with repeated ids keep the per-pair path (the exclusion set is keyed by
