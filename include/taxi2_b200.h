@@ -186,6 +186,10 @@ int taxi_format_aligned_pairs(const char* path, int32_t first_record,
                               int32_t x0, int32_t nx, int32_t ny,
                               const uint8_t* aln_x, const uint8_t* aln_y, const int64_t* aln_start, const int64_t* aln_off,
                               int32_t threads);
+/* n doubles as tab-separated text in the caller's buffer (the S^2 cells of the subset statistics files,
+   versus_all.py:143-249); returns the bytes written or -(bytes needed) if `capacity` is too small. */
+int64_t taxi_format_values(const double* values, int64_t n, const uint8_t* undefined, double scale,
+                           const char* float_format, const char* missing, char* out, int64_t capacity);
 /* SimpleAggregator state (sum, min, max, n, first-seen order) per (subset_x, subset_y), row-major order. */
 int taxi_aggregate_subsets(const double* metrics, const uint8_t* undefined, int32_t x0, int32_t nx, int32_t ny,
                            int32_t column, double scale, const int32_t* xsubset, const int32_t* ysubset, int32_t nsub,

@@ -60,6 +60,7 @@ SIGNATURES = {
                                      C.c_int32, C.c_double, C.c_char_p, C.c_char_p, C.c_int32]),
     "taxi_format_aligned_pairs": (C.c_int, [C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                             C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "taxi_format_values": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "taxi_aggregate_subsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "taxi_host_alloc": (C.c_void_p, [C.c_int64]),

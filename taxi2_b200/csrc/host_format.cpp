@@ -203,6 +203,25 @@ int taxi_format_pairs(const char* path, const int32_t* segments, int32_t nsegmen
     return format_rows(path, nx, threads, fn);
 }
 
+// n values as text, tab separated, into the caller's buffer: the float formatting of the subset
+// statistics files (versus_all.py:143-249), whose S^2 cells are formatted in one call per column.
+// Returns the bytes written, or -(bytes needed) when `capacity` is too small.
+int64_t taxi_format_values(const double* values, int64_t n, const uint8_t* undefined, double scale,
+                           const char* float_format, const char* missing, char* out, int64_t capacity)
+{
+    if (!values || n < 0 || !float_format || !missing || !out) return TAXI_E_ARG;
+    const ValueFormat vf(float_format);
+    std::string text;
+    text.reserve((size_t)n * 8);
+    for (int64_t k = 0; k < n; ++k) {
+        if (k) text += '\t';
+        append_value(text, values[k], undefined && undefined[k], scale, vf, missing);
+    }
+    if ((int64_t)text.size() > capacity) return -(int64_t)text.size();
+    std::memcpy(out, text.data(), text.size());
+    return (int64_t)text.size();
+}
+
 // One row per x: id, then one value per y (DistanceHandler.Matrix rows, distances.py:183-186)
 int taxi_format_matrix(const char* path, const char* xid_bytes, const int64_t* xid_off, int32_t x0, int32_t nx, int32_t ny,
                        const double* metrics, const uint8_t* undefined, int32_t column, double scale,

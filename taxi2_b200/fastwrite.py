@@ -92,6 +92,24 @@ def format_aligned_pairs(path, first_record: bool, xids: StringTable, yids: Stri
                                                _ptr(aln_start), _ptr(aln_off), threads))
 
 
+def format_values(values: np.ndarray, undefined: np.ndarray | None, fmt: str, missing: str, scale: float = 1.0) -> list[str]:
+    """[fmt % v or missing ...] for a vector of doubles, formatted by the library in one call."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    n = len(values)
+    if n == 0:
+        return []
+    und = None if undefined is None else np.ascontiguousarray(undefined, dtype=np.uint8)
+    cap = 24 * n + 64
+    while True:
+        buf = C.create_string_buffer(cap)
+        got = N.load().taxi_format_values(_ptr(values), n, _ptr(und), float(scale), fmt.encode(), missing.encode(), buf, cap)
+        if got >= 0:
+            return buf.raw[:got].decode("ascii").split("\t")
+        if got > -16:
+            N.check(int(got))
+        cap = -got + 64
+
+
 class NativeSubsetState:
     """sum / min / max / n / first-seen per (subset_x, subset_y) of one metric column."""
 

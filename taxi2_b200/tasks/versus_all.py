@@ -428,11 +428,10 @@ class NativeBlockWriter:
             agg = self.agg[name]
             if agg is None:
                 continue
-            subset_names = self.ids[name][2]
-            for metric, state in zip(self.metrics, self.states[name]):
-                target = agg.aggregators[str(metric)]
-                for (sx, sy), (mn, mx, mean, cnt) in state.items():
-                    target.set(subset_names[sx], subset_names[sy], mn, mx, mean, cnt)
+            # the subset files are written from the native states' arrays in one vectorised pass
+            # (SubsetAggregation.write_arrays); with S subsets they hold S^2 rows / cells, which the
+            # per-key Python objects of the handler path made the slowest part of a large task
+            agg.native = (self.ids[name][2], [str(m) for m in self.metrics], self.states[name])
 
 
 class SubsetAggregation:
@@ -449,7 +448,75 @@ class SubsetAggregation:
             self.aggregators[str(d.metric)].add(sx, sy, d.d)
         return (sx, sy)
 
+    native = None   # (subset names, metric labels, NativeSubsetState per metric) when the native aggregator ran
+
+    def write_arrays(self, path: Path, fmt) -> None:
+        """The same files as write(), from the arrays of the native aggregator (versus_all.py:143-249,
+        647-684): keys in first-seen order, mean / min / max per metric, "NA" where nothing was
+        defined; matrix rows are the runs of equal first subset in that order."""
+        names, labels, states = self.native
+        nsub = states[0].nsub
+        keys = np.nonzero(states[0].first_seen >= 0)[0]
+        keys = keys[np.argsort(states[0].first_seen[keys], kind="stable")]
+        kx, ky = keys // nsub, keys % nsub
+        label_of = ["?" if v is None else v for v in names]
+        tx = [label_of[k] for k in kx.tolist()]
+        ty = [label_of[k] for k in ky.tolist()]
+        form = fmt.float.format
+        fmtc = fastwrite.printf_format(fmt.float)
+
+        def column(values, counts):
+            if fmtc:   # plain float spec: the library formats the whole column in one call
+                return fastwrite.format_values(np.where(counts > 0, values, 0.0), counts == 0, fmtc, "NA")
+            return [form(v) if c else "NA" for v, c in zip(values.tolist(), counts.tolist())]
+
+        stats = []          # per metric: (mean, min, max) text columns over the keys
+        for st in states:
+            cnt = st.count[keys]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                mean = st.sum[keys] / cnt
+            stats.append((column(mean, cnt), column(st.min[keys], cnt), column(st.max[keys], cnt), cnt))
+        heads = [f"{label} {stat}" for label in labels for stat in ("mean", "min", "max")]
+        linear = path / "linear"
+        linear.mkdir(parents=True, exist_ok=True)
+        same = (kx == ky).tolist()
+        rows_pairs, rows_identity = [], []
+        columns = [col for st in stats for col in st[:3]]
+        for k, values in enumerate(zip(*columns)):
+            if same[k]:
+                rows_identity.append("\t".join((tx[k], *values)))
+            else:
+                rows_pairs.append("\t".join((tx[k], ty[k], *values)))
+        with open(linear / "pairs.tsv", "w", newline="") as f:
+            if rows_pairs:
+                f.write("\t".join(("target", "query", *heads)) + "\n" + "\n".join(rows_pairs) + "\n")
+        with open(linear / "identity.tsv", "w", newline="") as f:
+            if rows_identity:
+                f.write("\t".join(("target", *heads)) + "\n" + "\n".join(rows_identity) + "\n")
+        matricial = path / "matricial"
+        matricial.mkdir(parents=True, exist_ok=True)
+        # runs of equal first subset (the reference flushes a matrix row whenever idx changes)
+        starts = [0] + [k for k in range(1, len(keys)) if kx[k] != kx[k - 1]] + [len(keys)] if len(keys) else [0]
+        template = fmt.stats_template
+        import re
+        plain = re.match(r"^([^{}]*)\{mean\}([^{}]*)\{min\}([^{}]*)\{max\}([^{}]*)$", template)
+        for label, (mean, mn, mx, cnt) in zip(labels, stats):
+            has = cnt.tolist()
+            if plain:   # "{mean} ({min}-{max})" and the like: concatenation instead of 1e6 str.format calls
+                p0, p1, p2, p3 = plain.groups()
+                cells = [p0 + a + p1 + b + p2 + c + p3 if h else "NA" for a, b, c, h in zip(mean, mn, mx, has)]
+            else:
+                cells = [template.format(mean=a, min=b, max=c) if h else "NA" for a, b, c, h in zip(mean, mn, mx, has)]
+            with open(matricial / f"{label}.tsv", "w", newline="") as f:
+                for r in range(len(starts) - 1):
+                    lo, hi = starts[r], starts[r + 1]
+                    if r == 0:
+                        f.write("\t".join(("", *ty[lo:hi])) + "\n")
+                    f.write("\t".join((tx[lo], *cells[lo:hi])) + "\n")
+
     def write(self, path: Path, fmt) -> None:
+        if self.native is not None:
+            return self.write_arrays(path, fmt)
         # the subset writers of the reference keep their own default missing marker "NA"
         to_text = lambda v: "NA" if v is None else fmt.float.format(v)  # noqa: E731
         linear = path / "linear"
