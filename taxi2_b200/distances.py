@@ -9,6 +9,7 @@ NCD and BBC (alfpy, alignment-free compression / k-mer statistics) are out of sc
 from __future__ import annotations
 
 import re
+import threading
 from math import isinf, isnan
 from pathlib import Path
 from typing import Generator, Iterable, Literal, NamedTuple
@@ -50,21 +51,22 @@ class DistanceMetric(Type):
         return not (x is None or isnan(x) or isinf(x))
 
     # the four metrics of the pair seen last: every caller asks for them back to back on the same
-    # two strings (versus_all.py:546-552 and siblings), and one device call yields all four
-    _last_pair: tuple | None = None
-    _last_values = None
+    # two strings (versus_all.py:546-552 and siblings), and one device call yields all four.
+    # Per thread: two threads computing distances never see each other's pair.
+    _last = threading.local()
 
     def _calculate(self, x: str, y: str) -> float | None:
         if self.column is None:
             raise NotImplementedError()
-        if DistanceMetric._last_pair != (x, y):
+        last = DistanceMetric._last
+        if getattr(last, "pair", None) != (x, y):
             from .engine import default_engine
 
             eng = default_engine()
             eng.load([x, y], 0)
-            DistanceMetric._last_values = eng.count_pairs([0], [1], want=("metrics",))["metrics"][0].copy()
-            DistanceMetric._last_pair = (x, y)
-        value = float(DistanceMetric._last_values[self.column])
+            last.values = eng.count_pairs([0], [1], want=("metrics",))["metrics"][0].copy()
+            last.pair = (x, y)
+        value = float(last.values[self.column])
         return value if self._is_number(value) else None
 
     def calculate(self, x: Sequence, y: Sequence) -> Distance:
