@@ -104,6 +104,7 @@ struct AlignArgs {
     const int64_t* aln_off; int64_t* aln_start;
     uint8_t* trace; long long trace_per_warp; // traceback arena
     int32_t* bnd; long long bnd_per_warp;     // stripe-boundary rows (2 ints per column)
+    int32_t coop_stripes;                     // intra-task kernel: boundary buffers per CTA (the most stripes any pair of the launch has)
     unsigned long long* counter;              // dynamic work counter
     int* status;                              // sticky error flag
 };

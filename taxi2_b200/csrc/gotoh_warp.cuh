@@ -49,8 +49,15 @@ __device__ __forceinline__ int state_of_tag(int tag, const ScoreSet& sc)
     return tag == sc.pM ? 0 : (tag == sc.pX ? 1 : 2);
 }
 
-template <int H>
-__device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int lane, uint8_t* trace, int32_t* bnd)
+// COOP = false: the warp runs the stripes of its pair one after the other (inter-task: one pair per
+// warp).  COOP = true (intra-task, long pairs): the `nw` warps of a CTA share ONE pair -- warp `wid`
+// takes stripes wid, wid + nw, ... and the stripes run as a pipeline: stripe s + 1 follows stripe s
+// a few dozen columns behind, reading the bottom row of stripe s from that stripe's own boundary
+// buffer as soon as `progress[s]` (shared memory) says the column has been published.  The warp
+// that owns the last stripe then walks the path.  Same arithmetic, same trace layout.
+template <int H, bool COOP = false>
+__device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int lane, uint8_t* trace, int32_t* bnd,
+                                          int wid = 0, int nw = 1, volatile int* progress = nullptr)
 {
     using G = TraceGeom<H>;
     constexpr int HB = G::HB;
@@ -81,7 +88,11 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
     const int step_stride = nB + 31;
     int Hl[H];   // H(i, j-1) of my rows: best of the three states, tagged by the winning state
 
-    for (int s = 0; s < nstripes; ++s) {
+    for (int s = COOP ? wid : 0; s < nstripes; s += COOP ? nw : 1) {
+        // boundary rows: one buffer per warp (sequential stripes reuse it: the writer trails the
+        // reader by 31 columns), one per stripe when the stripes of a pair run concurrently
+        int32_t* bnd_in = COOP ? bnd + (size_t)max(s - 1, 0) * a.bnd_per_warp : bnd;
+        int32_t* bnd_out = COOP ? bnd + (size_t)s * a.bnd_per_warp : bnd;
         const int itop = s * SL + lane * H + 1;  // DP row held in register slot 0
         const int rows_here = min(SL, nA - s * SL);
         const int nlive = (rows_here + H - 1) / H;
@@ -113,7 +124,11 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                 nb = (int)__ldg(y + jj - 1);
                 if (lane == 0 && s > 0) {
                     TAXI_CHECK(a, 2LL * jj + 1 < a.bnd_per_warp, 11);
-                    nbX = __ldcg(bnd + 2 * jj); nbH = __ldcg(bnd + 2 * jj + 1);
+                    if (COOP) {
+                        while (progress[s - 1] < jj) { }      // the stripe above has not published this column yet
+                        __threadfence_block();
+                    }
+                    nbX = __ldcg(bnd_in + 2 * jj); nbH = __ldcg(bnd_in + 2 * jj + 1);
                 }
             }
         };
@@ -182,12 +197,21 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                 }
                 if (lane == 31 && s + 1 < nstripes) {
                     TAXI_CHECK(a, 2LL * j + 1 < a.bnd_per_warp, 13);
-                    __stcg(bnd + 2 * j, outX);
-                    __stcg(bnd + 2 * j + 1, outH);
+                    __stcg(bnd_out + 2 * j, outX);
+                    __stcg(bnd_out + 2 * j + 1, outH);
+                    if (COOP) {
+                        __threadfence_block();
+                        progress[s] = j;                       // columns 1..j of this stripe's bottom row are visible
+                    }
                 }
             }
         }
         __syncwarp();
+    }
+
+    if (COOP) {
+        __syncthreads();                               // every stripe of the pair is complete, its trace codes written
+        if ((nstripes - 1) % nw != wid) return;        // only the owner of the last stripe holds H(nA, nB) and walks the path
     }
 
     // ---- end state and score: H(nA, nB) sits in the register slot of row nA ------------------
@@ -303,6 +327,32 @@ gotoh_warp_kernel(const AlignArgs a)
         if (p >= (unsigned long long)a.npairs) break;
         align_one<H>(a, (long long)p, lane, trace, bnd);
         __syncwarp();
+    }
+}
+
+// Intra-task kernel for long pairs: one pair per CTA, its stripes pipelined over the CTA's warps.
+// Taken when a launch has fewer pairs than the GPU has resident warps and the pairs span several
+// stripes (a single 12 kbp x 9 kbp pair: 18 stripes over 8 warps instead of one warp doing all).
+constexpr int GOTOH_COOP_WARPS = 8;
+constexpr int GOTOH_COOP_MAX_STRIPES = 1024;
+
+template <int H>
+__global__ void __launch_bounds__(GOTOH_COOP_WARPS * 32, 1)
+gotoh_coop_kernel(const AlignArgs a)
+{
+    __shared__ volatile int progress[GOTOH_COOP_MAX_STRIPES];
+    __shared__ unsigned long long next_pair;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* trace = a.trace + (long long)blockIdx.x * a.trace_per_warp;                       // per CTA here
+    int32_t* bnd = a.bnd + (long long)blockIdx.x * a.bnd_per_warp * a.coop_stripes;             // one buffer per stripe
+    for (;;) {
+        __syncthreads();                                   // everyone is done with the previous pair (and its progress flags)
+        for (int k = threadIdx.x; k < GOTOH_COOP_MAX_STRIPES; k += blockDim.x) progress[k] = 0;
+        if (threadIdx.x == 0) next_pair = atomicAdd(a.counter, 1ULL);
+        __syncthreads();
+        const unsigned long long p = next_pair;
+        if (p >= (unsigned long long)a.npairs) break;
+        align_one<H, true>(a, (long long)p, lane, trace, bnd, wid, GOTOH_COOP_WARPS, progress);
     }
 }
 

@@ -116,6 +116,7 @@ struct taxi_ctx {
     int force_general = 0;          // option: always use the general int32 kernel
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
+    int no_coop = 0;                // option: never use the intra-task kernel for long pairs
     int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
@@ -174,18 +175,24 @@ template <int H> void launch_gotoh(const AlignArgs& a, int grid, cudaStream_t st
     gotoh_warp_kernel<H><<<grid, GOTOH_WARPS_PER_BLOCK * 32, 0, st>>>(a);
 }
 
+template <int H> void launch_coop(const AlignArgs& a, int grid, cudaStream_t st)
+{
+    gotoh_coop_kernel<H><<<grid, GOTOH_COOP_WARPS * 32, 0, st>>>(a);
+}
+
 struct Dispatch {
     int H;
     cudaError_t (*occ)(int*);
     void (*launch)(const AlignArgs&, int, cudaStream_t);
     int HB;
+    void (*coop)(const AlignArgs&, int, cudaStream_t) = nullptr;   // intra-task variant (general kernel only)
 };
 
 const Dispatch kDispatch[] = {
     {4, occupancy<4>, launch_gotoh<4>, TraceGeom<4>::HB},     {8, occupancy<8>, launch_gotoh<8>, TraceGeom<8>::HB},
     {12, occupancy<12>, launch_gotoh<12>, TraceGeom<12>::HB}, {16, occupancy<16>, launch_gotoh<16>, TraceGeom<16>::HB},
-    {21, occupancy<21>, launch_gotoh<21>, TraceGeom<21>::HB}, {24, occupancy<24>, launch_gotoh<24>, TraceGeom<24>::HB},
-    {32, occupancy<32>, launch_gotoh<32>, TraceGeom<32>::HB},
+    {21, occupancy<21>, launch_gotoh<21>, TraceGeom<21>::HB, launch_coop<21>}, {24, occupancy<24>, launch_gotoh<24>, TraceGeom<24>::HB, launch_coop<24>},
+    {32, occupancy<32>, launch_gotoh<32>, TraceGeom<32>::HB, launch_coop<32>},
 };
 
 // bytes -> 3-bit symbol codes through the context codebook, in the padded per-sequence layout of
@@ -411,8 +418,12 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     const long long work_units = fast ? a.nunits : a.npairs;
     c->last_kernel = fast ? 16 + mode : 32;
     a.f16 = f16;
-    // resident warps, capped by pairs and by a trace-arena budget of half the free memory
-    long long warps = (long long)c->sms * bps * GOTOH_WARPS_PER_BLOCK;
+    // Intra-task kernel: long pairs (several stripes) that are too few to occupy the GPU one pair per
+    // warp share a CTA each, the stripes of a pair pipelined over its warps (gotoh_coop_kernel).
+    const bool coop = !fast && !c->no_coop && d->coop != nullptr && nstripes >= 2 && nstripes <= GOTOH_COOP_MAX_STRIPES &&
+                      a.npairs * 4 <= (long long)c->sms * bps * GOTOH_WARPS_PER_BLOCK;
+    // resident warps (CTAs for the intra-task kernel), capped by pairs and by a trace-arena budget of half the free memory
+    long long warps = coop ? (long long)c->sms : (long long)c->sms * bps * GOTOH_WARPS_PER_BLOCK;
     size_t free_b = 0, total_b = 0;
     if ((long long)c->trace.cap >= warps * per_warp) free_b = 0;   // arena already large enough: no query
     else CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -420,20 +431,22 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     if (per_warp > budget) return fail(TAXI_E_NOMEM, "one pair needs %lld B of traceback arena, only %lld B available", per_warp, budget);
     warps = std::min(warps, std::max(1LL, budget / per_warp));
     warps = std::min(warps, work_units);
-    int grid = (int)((warps + GOTOH_WARPS_PER_BLOCK - 1) / GOTOH_WARPS_PER_BLOCK);
+    int grid = coop ? (int)std::max(warps, 1LL) : (int)((warps + GOTOH_WARPS_PER_BLOCK - 1) / GOTOH_WARPS_PER_BLOCK);
     grid = std::max(grid, 1);
-    const long long gw = (long long)grid * GOTOH_WARPS_PER_BLOCK;
+    const long long gw = coop ? (long long)grid : (long long)grid * GOTOH_WARPS_PER_BLOCK;
     CUDA_TRY(c->trace.reserve((size_t)(gw * per_warp)));
-    CUDA_TRY(c->bnd.reserve((size_t)(gw * bnd_per_warp)));
+    CUDA_TRY(c->bnd.reserve((size_t)(gw * bnd_per_warp * (coop ? nstripes : 1))));
     CUDA_TRY(c->counter.reserve(1));
-    CUDA_TRY(c->status.reserve(1));
     CUDA_TRY(cudaMemsetAsync(c->counter.p, 0, sizeof(unsigned long long), c->stream));
+    a.coop_stripes = (int32_t)nstripes;
+    if (coop) c->last_kernel = 33;
     a.sc = c->sc;
     a.trace = c->trace.p; a.trace_per_warp = per_warp;
     a.bnd = c->bnd.p; a.bnd_per_warp = bnd_per_warp;
     a.counter = c->counter.p; a.status = c->status.p;
     if (record_start) CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    d->launch(a, grid, c->stream);
+    if (coop) d->coop(a, grid, c->stream);
+    else d->launch(a, grid, c->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     c->launches += 1;
@@ -1187,6 +1200,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
     if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
     if (std::strcmp(key, "count_kernel") == 0) { c->count_kernel = value; return TAXI_OK; }
+    if (std::strcmp(key, "no_coop") == 0) { c->no_coop = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }
 

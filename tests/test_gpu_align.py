@@ -634,3 +634,39 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
     want = oracle.count_pairs(data, off, px, py + (nx if ys is not None else 0))
     assert np.array_equal(results[2]["counts"][px, py], want["counts"])
     assert_metrics_close(results[2]["metrics"][px, py], want["metrics"])
+
+
+def test_intra_task_kernel_for_few_long_pairs(engine):
+    """A handful of pairs spanning many stripes: the stripes of each pair are pipelined over the
+    warps of a CTA (gotoh_coop_kernel) instead of one warp running them all.  Same scores, counts
+    and alignment strings as the one-pair-per-warp kernel and as the oracle, under a Gotoh and a
+    Needleman-Wunsch score set, including pairs with fewer stripes than warps and a 1-column y."""
+    rng = np.random.default_rng(4000)
+    xs, ys = random_pairs(rng, 5, 2200, 5200, sub=0.1, indel=0.02)
+    xs += [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 3000)), b"ACGTTGCA" * 90, xs[0]]
+    ys += [b"G", ys[1], ys[0][:700]]
+    px = np.arange(len(xs), dtype=np.int32)
+    for scores in [(2, -1, -3, -2, -1, -1), (2, -3, -4, -4, -4, -4)]:
+        want = oracle_batch(xs, ys, px, px, scores)
+        got = {}
+        for no_coop in (0, 1):
+            engine.set_option("no_coop", no_coop)
+            engine.set_option("force_general", 1)
+            try:
+                engine.set_scores(scores)
+                engine.load(xs, 0)
+                engine.load(ys, 1)
+                res = engine.align_pairs(px, px)
+                assert engine.last_kernel == (32 if no_coop else 33)
+                ax, ay, sc = engine.align_strings(px, px)
+            finally:
+                engine.set_option("no_coop", 0)
+                engine.set_option("force_general", 0)
+            got[no_coop] = (res, ax, ay, sc)
+            assert np.array_equal(res["score"], want["score"]) and np.array_equal(res["counts"], want["counts"])
+            assert_metrics_close(res["metrics"], want["metrics"])
+            assert np.array_equal(sc, want["score"])
+        assert got[0][1] == got[1][1] and got[0][2] == got[1][2]
+        for k in (0, 5, 6):
+            ox, oy, _ = oracle.align(xs[k], ys[k], scores)
+            assert got[0][1][k].decode() == ox and got[0][2][k].decode() == oy
