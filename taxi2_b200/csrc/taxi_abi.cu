@@ -386,6 +386,14 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
         a.nunits = (a.npairs / a.ny) * (((long long)a.ny + 1) / 2);   // whole rows: npairs = rows * ny
     }
     if (!fast) H = pick_H(max_rows);
+    // few long pairs: the intra-task kernel wants tall stripes (its variants are the 21 / 24 / 32-row ones)
+    if (!fast && !c->no_coop && max_rows > 2 * 32 * 21 && a.npairs * 4 <= (long long)c->sms * 3 * GOTOH_WARPS_PER_BLOCK) {
+        long long best = -1;
+        for (int h : {21, 24, 32}) {
+            const long long sl = 32LL * h, slots = (max_rows + sl - 1) / sl * sl;
+            if (best < 0 || slots < best || (slots == best && h > H)) { best = slots; H = h; }
+        }
+    }
     const Dispatch* d = nullptr;
     if (fast) {
         if (mode == 2) { for (const auto& e : kDispatch16m) if (e.H == H) d = &e; }

@@ -60,7 +60,7 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
             got = engine.align_pairs(px, px)
             kernels.add(engine.last_kernel)
             if force_general:
-                assert engine.last_kernel == 32
+                assert engine.last_kernel in (32, 33)      # 33 = the intra-task variant (few pairs spanning several stripes)
             assert np.array_equal(got["score"], want["score"])
             assert np.array_equal(got["counts"], want["counts"])
             assert_metrics_close(got["metrics"], want["metrics"])
@@ -76,7 +76,7 @@ def check_pairs(engine, xs, ys, scores, strings=True, expect_fast=None):
     if expect_fast is True:
         assert kernels & {16, 17, 18}, "packed fast path was expected to be eligible"
     if expect_fast is False:
-        assert kernels == {32}
+        assert kernels <= {32, 33}
 
 
 @pytest.mark.parametrize("case", ALIGN["align_tests"] + ALIGN["align_tests_failing"],
