@@ -214,6 +214,8 @@ void taxi_host_free(void* p);
  * 48 = a rectangle whose rows were grouped by length into several launches; after an alignment-free
  * call: 8 = popcount kernel, 9 = tensor-core kernel.  "count_kernel" = 1 / 2 forces the popcount /
  * the tensor-core kernel for alignment-free rectangles (0 = whichever fits; tests compare the two).
+ * 33 = gotoh_warp's intra-task variant (few pairs spanning several stripes: one pair per CTA, its
+ * stripes pipelined over the warps); "no_coop" = 1 keeps such launches on the one-pair-per-warp kernel.
  */
 int taxi_set_option(taxi_ctx* ctx, const char* key, int value);
 int taxi_last_kernel(taxi_ctx* ctx);

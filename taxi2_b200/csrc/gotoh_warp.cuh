@@ -333,7 +333,7 @@ gotoh_warp_kernel(const AlignArgs a)
 // Intra-task kernel for long pairs: one pair per CTA, its stripes pipelined over the CTA's warps.
 // Taken when a launch has fewer pairs than the GPU has resident warps and the pairs span several
 // stripes (a single 12 kbp x 9 kbp pair: 18 stripes over 8 warps instead of one warp doing all).
-constexpr int GOTOH_COOP_WARPS = 8;
+constexpr int GOTOH_COOP_WARPS = 12;
 constexpr int GOTOH_COOP_MAX_STRIPES = 1024;
 
 template <int H>
