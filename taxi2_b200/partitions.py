@@ -28,28 +28,30 @@ class Partition(dict):
 
 
 class PartitionHandler(FileHandler[Classification]):
+    """Read-only handlers yielding Classification(individual, subset); an optional `filter`
+    rewrites every classification or drops it by returning None (partitions.py:30-66)."""
+
+    filter: Callable | None = None
+
     @classmethod
     def as_dict(cls, path: Path, *args, **kwargs) -> Partition:
-        partition = Partition()
-        for individual, subset in cls(path, "r", *args, **kwargs):
-            partition[individual] = subset
-        return partition
+        # later rows win, as in a dict built by assignment
+        return Partition({c.individual: c.subset for c in map(Classification._make, cls(path, "r", *args, **kwargs))})
 
     def _open(self, path: Path, mode: Literal["r", "w"] = "r", filter: Callable = None, *args, **kwargs):
         self.filter = filter
         super()._open(path, mode, *args, **kwargs)
 
     def _iter_write(self) -> WriteHandle[Classification]:
-        raise NotImplementedError()
+        raise NotImplementedError("partitions are read-only here")
 
     def _iter_read(self, *args, **kwargs) -> ReadHandle[Classification]:
-        inner = self._iter_read_inner(*args, **kwargs)
-        yield next(inner)
-        for classification in inner:
-            if self.filter:
-                classification = self.filter(classification)
-            if classification is not None:
-                yield classification
+        source = self._iter_read_inner(*args, **kwargs)
+        yield next(source)                     # the handler itself, once the file is open
+        if self.filter is None:
+            yield from source
+            return
+        yield from (kept for kept in map(self.filter, source) if kept is not None)
 
     @abstractmethod
     def _iter_read_inner(self, *args, **kwargs) -> ReadHandle[Classification]:
