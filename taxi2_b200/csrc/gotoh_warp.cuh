@@ -119,13 +119,16 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
         // stripe left in the boundary buffer are fetched one step ahead: their latency hides behind a
         // whole step instead of stalling the warp at the top of it
         int nb = 0, nbX = 0, nbH = 0;
+        int seen = 0;                                  // COOP: columns of the stripe above known to be published
         auto fetch_next = [&](int jj) {
             if (live && jj >= 1 && jj <= nB) {
                 nb = (int)__ldg(y + jj - 1);
                 if (lane == 0 && s > 0) {
                     TAXI_CHECK(a, 2LL * jj + 1 < a.bnd_per_warp, 11);
-                    if (COOP) {
-                        while (progress[s - 1] < jj) { }      // the stripe above has not published this column yet
+                    if (COOP && jj > seen) {                   // poll only when the last look did not already cover this column
+                        int got;
+                        while ((got = progress[s - 1]) < jj) { }   // the stripe above has not published this column yet
+                        seen = got;
                         __threadfence_block();
                     }
                     nbX = __ldcg(bnd_in + 2 * jj); nbH = __ldcg(bnd_in + 2 * jj + 1);
@@ -199,7 +202,7 @@ __device__ __forceinline__ void align_one(const AlignArgs& a, long long p, int l
                     TAXI_CHECK(a, 2LL * j + 1 < a.bnd_per_warp, 13);
                     __stcg(bnd_out + 2 * j, outX);
                     __stcg(bnd_out + 2 * j + 1, outH);
-                    if (COOP) {
+                    if (COOP && ((j & 7) == 0 || j == nB)) {   // publish every 8th column (and the last): one fence per 8 steps
                         __threadfence_block();
                         progress[s] = j;                       // columns 1..j of this stripe's bottom row are visible
                     }
