@@ -93,6 +93,25 @@ int taxi_align_rect_device(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, in
 int taxi_sync(taxi_ctx* ctx);
 
 /*
+ * Both orientations of a rectangle from (almost) one alignment per unordered pair: versusAll aligns
+ * (x, y) AND (y, x) (versus_all.py:746).  d_* receive the nx x ny results of (x, y), t_* the ny x nx
+ * results of (y, x) (all device pointers).  The dynamic programme of (y, x) is the transpose of that
+ * of (x, y); the first alignment differs only where Ix and Iy tie on the traced path, which the kernel
+ * detects -- those pairs (taxi_last_redo() of them, 0.7 % of COI barcodes) are re-aligned the other
+ * way round, the rest mirror their result.  Bit-identical to two taxi_align_rect_device calls.
+ * Synchronous.
+ */
+int taxi_align_rect_both_device(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                                int32_t* d_score, int32_t* d_counts, double* d_metrics,
+                                int32_t* t_score, int32_t* t_counts, double* t_metrics);
+/* Host buffers: (x, y) results with a row stride of ld_xy pairs, (y, x) results with a row stride of
+   ld_yx pairs -- a tile and its mirror can be written straight into their places of one matrix. */
+int taxi_align_rect_both(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                         int32_t* out_score, int32_t* out_counts, double* out_metrics, int64_t ld_xy,
+                         int32_t* tout_score, int32_t* tout_counts, double* tout_metrics, int64_t ld_yx);
+int64_t taxi_last_redo(taxi_ctx* ctx);
+
+/*
  * Gapped strings (align.py:151-157 return value).  aln_offsets[npairs+1] are exclusive prefix
  * sums of the capacities len(x)+len(y) (computed by taxi_alignment_capacity); each alignment is
  * written right-aligned inside its slot of out_x / out_y and aln_start[p] receives the index of

@@ -102,6 +102,11 @@ struct AlignArgs {
     double* metrics;                          // [npairs][4] or nullptr
     uint8_t* aln_x; uint8_t* aln_y;           // gapped strings (right-aligned in slots) or nullptr
     const int64_t* aln_off; int64_t* aln_start;
+    // "both orientations" launches (SYM kernels): results of (y, x) are the results of (x, y) unless a
+    // tie between Ix and Iy was decided on the traced path; then the pair is appended to `redo`
+    int32_t nx;                               // rows of the rectangle (transposed index = col * nx + row)
+    int32_t* t_score; int32_t* t_counts; double* t_metrics;   // [ny][nx] outputs of the mirrored pairs, or nullptr
+    long long* redo; unsigned long long* redo_count;          // out indices of orientation-sensitive pairs
     uint8_t* trace; long long trace_per_warp; // traceback arena
     int32_t* bnd; long long bnd_per_warp;     // stripe-boundary rows (2 ints per column)
     int32_t coop_stripes;                     // intra-task kernel: boundary buffers per CTA (the most stripes any pair of the launch has)

@@ -94,9 +94,11 @@ struct Walk {
     int n, same, ts;                      // per-lane partial counts (both-real, identical, transitions)
     int gapc, pend;                       // warp-uniform: gap columns inside / after the both-real span so far
     bool seen;
+    bool sens;                            // SYM: a tie between Ix and Iy was decided on the path: (y, x) may align differently
     int64_t wpos;                         // write cursor of the gapped strings
     int score;
     int tb, ca, cb;                       // the window element this lane holds: traceback code, x / y symbol codes
+    int nA0, nB0;                         // the end cell (SYM: the path starts there in the state that wins it)
 };
 
 // address of the traceback code of cell (ii, jj); MULTI = arena with several stripes
@@ -127,6 +129,7 @@ __device__ __forceinline__ void walk_fetch(const AlignArgs& a, Walk& w, int lane
     }
 }
 
+template <bool SYM = false>
 __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int lane)
 {
     if (!(w.i > 0 && w.j > 0)) return;   // warp-uniform
@@ -142,6 +145,15 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     const unsigned cont = __ballot_sync(TAXI_FULL_MASK, ns == state);
     const int V = min(__ffs(~cont | 0x80000000u), nvalid);   // cells visited: up to and including the first hand-over
     const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
+    if (SYM) {
+        // Orientation.  The path of (y, x) is the transpose of this one unless the winner of H at a
+        // cell the path enters is Ix with Iy at the same score (Biopython prefers Ix; transposed, the
+        // roles swap).  Bit 4 of a cell's code says so for that cell.  The path enters cells in their
+        // H state after a diagonal move (the cell behind the last visited one, lane V) and at the start.
+        const int behind = __shfl_sync(TAXI_FULL_MASK, tb, V & 31);
+        if (state == 0 && next == 1 && V < 32 && (behind & 16)) w.sens = true;
+        if (state == 1 && w.i == (int)w.nA0 && w.j == (int)w.nB0 && (__shfl_sync(TAXI_FULL_MASK, tb, 0) & 16)) w.sens = true;
+    }
     const bool mine = lane < V;
     const unsigned visited = 0xffffffffu >> (32 - V);
     const Fast16& f = a.f16;
@@ -184,6 +196,7 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     w.state = next;
 }
 
+template <bool SYM = false>
 __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lane)
 {
     if (a.aln_x != nullptr) {
@@ -208,12 +221,29 @@ __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lan
     if (lane != 0) return;
     if (a.score) a.score[w.p] = w.score;
     if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * w.p) = make_int4(same, ts, tv, w.gapc);
+    double m[4];
+    if (a.metrics || (SYM && a.t_metrics)) metrics_from_counts(same, ts, tv, w.gapc, m);
     if (a.metrics) {
-        double m[4];
-        metrics_from_counts(same, ts, tv, w.gapc, m);
         double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * w.p);
         dst[0] = make_double2(m[0], m[1]);
         dst[1] = make_double2(m[2], m[3]);
+    }
+    if (SYM) {
+        // the mirrored pair (y, x): same score, counts and metrics, at the transposed position -- unless the
+        // path was orientation-sensitive, in which case the host re-aligns (y, x) on its own
+        if (w.sens) {
+            const unsigned long long k = atomicAdd(a.redo_count, 1ULL);
+            a.redo[k] = w.p;
+        } else {
+            const long long t = (w.p % a.ny) * (long long)a.nx + w.p / a.ny;
+            if (a.t_score) a.t_score[t] = w.score;
+            if (a.t_counts) *reinterpret_cast<int4*>(a.t_counts + 4 * t) = make_int4(same, ts, tv, w.gapc);
+            if (a.t_metrics) {
+                double2* dst = reinterpret_cast<double2*>(a.t_metrics + 4 * t);
+                dst[0] = make_double2(m[0], m[1]);
+                dst[1] = make_double2(m[2], m[3]);
+            }
+        }
     }
 }
 
@@ -223,25 +253,26 @@ __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, cons
     Walk w;
     w.x = x; w.y = y; w.p = p; w.i = nA; w.j = nB; w.state = 3 - (int)(fin & 3u);
     w.half = half; w.off = off; w.stride = stride;
-    w.n = w.same = w.ts = w.gapc = w.pend = 0; w.seen = false;
+    w.n = w.same = w.ts = w.gapc = w.pend = 0; w.seen = false; w.sens = false;
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
     w.tb = w.ca = w.cb = 0;
+    w.nA0 = nA; w.nB0 = nB;
     return w;
 }
 
-template <int H, bool MULTI>
+template <int H, bool MULTI, bool SYM = false>
 __device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, const uint8_t* trace, int l0, Walk& wa, Walk& wb, bool second)
 {
     if (!second) { wb.i = 0; wb.j = 0; }
     while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
         walk_fetch<H, MULTI>(a, wa, lane, trace, l0);
         walk_fetch<H, MULTI>(a, wb, lane, trace, l0);
-        walk_advance(wa, a, lane);
-        walk_advance(wb, a, lane);
+        walk_advance<SYM>(wa, a, lane);
+        walk_advance<SYM>(wb, a, lane);
     }
-    walk_finish(wa, a, lane);
-    if (second) walk_finish(wb, a, lane);
+    walk_finish<SYM>(wa, a, lane);
+    if (second) walk_finish<SYM>(wb, a, lane);
 }
 
 struct PairRef {
@@ -386,7 +417,9 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
 // reproduces the leading end gap by itself (requires internal extend == end extend, checked on
 // the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
 // infinity".
-template <int H>
+// SYM: every cell's code also says (bit 4) whether H was won by Ix with Iy at the same score -- the one
+// decision that differs when the pair is aligned the other way round; see walk_advance.
+template <int H, bool SYM = false>
 __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
 {
     constexpr int HB = Pair16Geom<H>::HB;
@@ -473,11 +506,17 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                     uint32_t Mr_next = 0;
                     if (r + 1 < H) Mr_next = diag_candidate(Hl[r], a2[r + 1], b2, f.negD);   // needs H(i, j-1) before it is overwritten
                     const uint32_t Yin = Yn[r];
-                    const uint32_t tc = lop3_or3(Mr, Xin, Yin);
+                    uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
                     const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
                     const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
                     Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
+                    if constexpr (SYM) {
+                        // H - Yt per half is 1 exactly when Ix won (tag 2) against Iy at the same score (tag 1);
+                        // min(., 2) * 16 puts that in bit 4 of the cleaned code (IADD + VIMNMX + IMAD + LOP3)
+                        const uint32_t tie16 = __vminu2(Hl[r] - Yt, 0x00020002u) * 16u;
+                        tc = lop3_and_or(tc, 0x000F000Fu, tie16);
+                    }
                     Xin = __viaddmax_u16x2(Mt, ncXM, Xt + cXX);
                     Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt + ((r == H - 1) ? cYYl : cYYi));
                     if (r & 1) tw[r >> 1] = __byte_perm(tprev, tc, 0x6420);
@@ -508,7 +547,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
 
     Walk wa = walk_start(a, A.out, A.xc, A.yc, A.nA, A.nB, 0, offA, finA, f.beta, f.bias);
     Walk wb = walk_start(a, B.out, B.xc, B.yc, B.nA, B.nB, 1, offB, finB, f.beta, f.bias);
-    traceback_two<H, false>(a, lane, trace, l0, wa, wb, p1 != p0);
+    traceback_two<H, false, SYM>(a, lane, trace, l0, wa, wb, p1 != p0);
 }
 
 // Multi-stripe form of the bottom-aligned variant for x longer than 32*H - 1: the slots are cut
@@ -669,7 +708,7 @@ constexpr int PAIR16_WARPS_PER_BLOCK = PAIR16_WPB;
 // MODE 0: top-aligned rows; 1: bottom-aligned rows; 2: bottom-aligned, several stripes (long x)
 // Three blocks of four warps (168 registers) is the measured optimum for the 21-row kernel; the
 // taller / multi-stripe instantiations need more registers and run two blocks per SM.
-template <int H, int MODE>
+template <int H, int MODE, bool SYM = false>
 __global__ void __launch_bounds__(PAIR16_WARPS_PER_BLOCK * 32, (H >= 32) ? 2 : PAIR16_MIN_BLOCKS)
 gotoh_pair16_kernel(const AlignArgs a)
 {
@@ -693,7 +732,7 @@ gotoh_pair16_kernel(const AlignArgs a)
             p1 = (2ULL * cu + 1ULL < (unsigned long long)a.ny) ? p0 + 1 : p0;
         }
         if constexpr (MODE == 2) align_two_bottom_multi<H>(a, p0, p1, lane, trace, bnd);
-        else if constexpr (MODE == 1) align_two_bottom<H>(a, p0, p1, lane, trace);
+        else if constexpr (MODE == 1) align_two_bottom<H, SYM>(a, p0, p1, lane, trace);
         else align_two<H>(a, p0, p1, lane, trace);
         (void)bnd;
         __syncwarp();

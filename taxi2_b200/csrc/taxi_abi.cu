@@ -130,11 +130,16 @@ struct taxi_ctx {
     DevBuf<double> d_metrics;
     DevBuf<uint8_t> d_alnx, d_alny;
     DevBuf<int64_t> d_alnoff, d_alnstart;
+    DevBuf<long long> d_redo;
+    DevBuf<int32_t> d_rscore, d_rcounts;   // results of the re-aligned mirrored pairs before they are scattered
+    DevBuf<double> d_rmetrics;
+    DevBuf<unsigned long long> d_redo_count;
     DevBuf<int32_t> d_argidx, d_bestcounts;
     DevBuf<double> d_argval, d_bestmetrics;
     // stats of the last call
     int64_t launches = 0, cells = 0;
     double kernel_ms = 0.0;
+    int64_t last_redo = 0;          // pairs the last "both orientations" call had to re-align
 };
 
 namespace {
@@ -222,6 +227,16 @@ template <int H, int MODE> void launch_pair16(const AlignArgs& a, int grid, cuda
     gotoh_pair16_kernel<H, MODE><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
 }
 
+template <int H> cudaError_t occupancy16s(int* blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gotoh_pair16_kernel<H, 1, true>, PAIR16_WARPS_PER_BLOCK * 32, 0);
+}
+
+template <int H> void launch_pair16s(const AlignArgs& a, int grid, cudaStream_t st)
+{
+    gotoh_pair16_kernel<H, 1, true><<<grid, PAIR16_WARPS_PER_BLOCK * 32, 0, st>>>(a);
+}
+
 #define P16(H, M) {H, occupancy16<H, M>, launch_pair16<H, M>, Pair16Geom<H>::HB}
 const Dispatch kDispatch16[] = {P16(8, 0), P16(12, 0), P16(16, 0), P16(21, 0), P16(24, 0), P16(32, 0)};
 // bottom-aligned rows (needs internal extend == end extend and one spare row slot)
@@ -229,6 +244,10 @@ const Dispatch kDispatch16b[] = {P16(8, 1), P16(12, 1), P16(16, 1), P16(21, 1), 
 // ... in several stripes, for x longer than one stripe
 const Dispatch kDispatch16m[] = {P16(16, 2), P16(21, 2), P16(24, 2), P16(32, 2)};
 #undef P16
+// bottom-aligned, "both orientations" (the code of every cell also records Ix / Iy ties, the walk mirrors the result)
+#define P16S(H) {H, occupancy16s<H>, launch_pair16s<H>, Pair16Geom<H>::HB}
+const Dispatch kDispatch16s[] = {P16S(8), P16S(12), P16S(16), P16S(21), P16S(24), P16S(32)};
+#undef P16S
 
 // Packed 16-bit fast path: is it EXACT for this score set and these lengths?  (gotoh_pair16.cuh)
 // dead_extra: largest difference between the x lengths of the two pairs of a warp unit (0 for
@@ -361,7 +380,10 @@ int build_units(taxi_ctx* c, long long npairs, long long max_dead)
 // Enqueue one alignment launch.  All pointers in `a` other than scratch are already device
 // pointers.  max_rows / max_cols bound the lengths of the x / y sequences touched.  Pair-list
 // launches (a.px set) expect the lengths of every pair in c->h_la / c->h_lb (upload_pairs).
-int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool record_start = true, bool reset_work = true)
+// sym: the caller wants the "both orientations" kernel (a.t_* / a.redo set); *sym_used tells whether this launch could
+// provide it (packed, bottom-aligned, one stripe) -- if not, nothing is launched and the caller falls back.
+int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool record_start = true, bool reset_work = true,
+                  bool sym = false, bool* sym_used = nullptr)
 {
     Fast16 f16{};
     int H = 0;
@@ -395,7 +417,13 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
         }
     }
     const Dispatch* d = nullptr;
-    if (fast) {
+    if (sym) {
+        const bool ok = fast && mode == 1 && !a.px;
+        if (sym_used) *sym_used = ok;
+        if (!ok) return TAXI_OK;
+        for (const auto& e : kDispatch16s) if (e.H == H) d = &e;
+    }
+    else if (fast) {
         if (mode == 2) { for (const auto& e : kDispatch16m) if (e.H == H) d = &e; }
         else { for (const auto& e : (mode == 1 ? kDispatch16b : kDispatch16)) if (e.H == H) d = &e; }
     }
@@ -424,7 +452,7 @@ int enqueue_align(taxi_ctx* c, AlignArgs a, int max_rows, int max_cols, bool rec
     const long long per_warp = ((nstripes * (arena_cols + 31LL) * 32 * d->HB) + 255) / 256 * 256;
     const long long bnd_per_warp = 2LL * (arena_cols + 2);
     const long long work_units = fast ? a.nunits : a.npairs;
-    c->last_kernel = fast ? 16 + mode : 32;
+    c->last_kernel = sym ? 20 : (fast ? 16 + mode : 32);
     a.f16 = f16;
     // Intra-task kernel: long pairs (several stripes) that are too few to occupy the GPU one pair per
     // warp share a CTA each, the stripes of a pair pipelined over its warps (gotoh_coop_kernel).
@@ -623,7 +651,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
     c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_units.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
-    c->d_argidx.release(); c->d_argval.release(); c->d_bestcounts.release(); c->d_bestmetrics.release();
+    c->d_redo.release(); c->d_redo_count.release(); c->d_rscore.release(); c->d_rcounts.release(); c->d_rmetrics.release(); c->d_argidx.release(); c->d_argval.release(); c->d_bestcounts.release(); c->d_bestmetrics.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -837,6 +865,32 @@ int taxi_align_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     return enqueue_align(c, a, mr, mc);
 }
 
+// results of a re-aligned list of mirrored pairs -> their transposed positions
+__global__ void scatter_redo_kernel(const long long* __restrict__ redo, long long n, int32_t nx, int32_t ny,
+                                    const int32_t* __restrict__ score, const int32_t* __restrict__ counts, const double* __restrict__ metrics,
+                                    int32_t* __restrict__ t_score, int32_t* __restrict__ t_counts, double* __restrict__ t_metrics)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long p = redo[k], t = (p % ny) * (long long)nx + p / ny;
+    if (t_score) t_score[t] = score[k];
+    if (t_counts) *reinterpret_cast<int4*>(t_counts + 4 * t) = *reinterpret_cast<const int4*>(counts + 4 * k);
+    if (t_metrics) {
+        reinterpret_cast<double2*>(t_metrics + 4 * t)[0] = reinterpret_cast<const double2*>(metrics + 4 * k)[0];
+        reinterpret_cast<double2*>(t_metrics + 4 * t)[1] = reinterpret_cast<const double2*>(metrics + 4 * k)[1];
+    }
+}
+
+// AlignArgs with the roles of the two sets exchanged: rows from the y set, columns from the x set
+void fill_swapped(AlignArgs& a, const taxi_ctx* c)
+{
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    a.xb = Y.bytes.p; a.xoff = Y.d_off.p; a.xc = Y.codes.p;
+    a.yb = X.bytes.p; a.yoff = X.d_off.p; a.yc = X.codes.p;
+    a.px = a.py = nullptr; a.xrows = nullptr; a.ycols = nullptr;
+}
+
 // Host-facing rectangles of any size: the device-side result buffers hold at most kChunkPairs
 // pairs, so a large rectangle (BASELINE C3 is 2.5e9 ordered pairs = 120 GB of results) is walked
 // in blocks of whole rows, each downloaded into its place of the caller's arrays.
@@ -864,6 +918,143 @@ int taxi_align_rect(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny,
                                    out_metrics ? out_metrics + 4 * at : nullptr))) return rc;
         if ((rc = finish_align(c))) return rc;
     }
+    return TAXI_OK;
+}
+
+// Both orientations of a rectangle: (x, y) into d_* ([nx][ny]) and (y, x) into t_* ([ny][nx]).
+// The DP of (y, x) is the transpose of the DP of (x, y) (the six scores treat the two sequences
+// alike); only the choice between Ix and Iy at equal score differs, and the "both orientations"
+// kernel notes on the traced path whether such a choice was ever made.  Pairs without one (99.3 % of
+// COI barcodes) get their mirrored result for free; the others are re-aligned the other way round.
+// Synchronous (the list of pairs to re-align is read back).  Falls back to two ordinary launches
+// when the packed bottom-aligned kernel is not eligible or the rows need several geometries.
+int taxi_align_rect_both_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                                int32_t* d_score, int32_t* d_counts, double* d_metrics,
+                                int32_t* t_score, int32_t* t_counts, double* t_metrics)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    ON_DEVICE(c->device);
+    const long long npairs = (long long)nx * ny;
+    if (npairs == 0) return TAXI_OK;
+    const SeqSet& X = c->set[0];
+    const SeqSet& Y = yset(c);
+    if (has_empty(X, x0, nx) || has_empty(Y, y0, ny)) return fail(TAXI_E_EMPTY, "sequence has zero length");
+    const int mr = max_len_range(X, x0, nx), mc = max_len_range(Y, y0, ny);
+    if ((rc = range_check(c, mr, mc))) return rc;
+    int lo = INT32_MAX;
+    for (int32_t i = x0; i < x0 + nx; ++i) lo = std::min<int>(lo, (int)(X.off[i + 1] - X.off[i]));
+    AlignArgs a{};
+    fill_rect(a, c, x0, y0, ny, npairs);
+    a.nx = nx;
+    a.score = (flags & TAXI_OUT_SCORE) ? d_score : nullptr;
+    a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
+    a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
+    a.t_score = (flags & TAXI_OUT_SCORE) ? t_score : nullptr;
+    a.t_counts = (flags & TAXI_OUT_COUNTS) ? t_counts : nullptr;
+    a.t_metrics = (flags & TAXI_OUT_METRICS) ? t_metrics : nullptr;
+    CUDA_TRY(c->d_redo.reserve((size_t)npairs, 1));
+    CUDA_TRY(c->d_redo_count.reserve(1));
+    CUDA_TRY(cudaMemsetAsync(c->d_redo_count.p, 0, sizeof(unsigned long long), c->stream));
+    a.redo = c->d_redo.p; a.redo_count = c->d_redo_count.p;
+    bool sym_used = false;
+    // rows of very different length would be split over several kernel geometries: leave those to the ordinary path
+    if (lo * 2 > mr && (rc = enqueue_align(c, a, mr, mc, true, true, true, &sym_used))) return rc;
+    if (!sym_used) {
+        // fallback: two ordinary launches, the second with the roles of the sets exchanged
+        if ((rc = taxi_align_rect_device(c, x0, nx, y0, ny, flags, d_score, d_counts, d_metrics))) return rc;
+        if ((rc = finish_align(c))) return rc;
+        AlignArgs b{};
+        fill_swapped(b, c);
+        b.x0 = y0; b.y0 = x0; b.ny = nx; b.npairs = npairs;
+        b.score = a.t_score; b.counts = a.t_counts; b.metrics = a.t_metrics;
+        c->cells += cells_rect(X, Y, x0, nx, y0, ny);
+        if ((rc = enqueue_align(c, b, mc, mr))) return rc;
+        return finish_align(c);
+    }
+    c->cells += cells_rect(X, Y, x0, nx, y0, ny);
+    if ((rc = finish_align(c))) return rc;
+    unsigned long long nredo = 0;
+    CUDA_TRY(cudaMemcpy(&nredo, c->d_redo_count.p, sizeof nredo, cudaMemcpyDeviceToHost));
+    c->last_redo = (int64_t)nredo;
+    if (nredo == 0) return TAXI_OK;
+    // re-align the orientation-sensitive pairs as (y, x): rows from the y set, columns from the x set
+    std::vector<long long> redo((size_t)nredo);
+    CUDA_TRY(cudaMemcpy(redo.data(), c->d_redo.p, (size_t)nredo * sizeof(long long), cudaMemcpyDeviceToHost));
+    std::sort(redo.begin(), redo.end());                       // launch order independent of the atomics
+    std::vector<int32_t> px((size_t)nredo), py((size_t)nredo);
+    c->h_la.resize((size_t)nredo); c->h_lb.resize((size_t)nredo);
+    int rmr = 0, rmc = 0;
+    long long cells = 0;
+    for (size_t k = 0; k < redo.size(); ++k) {
+        const int32_t xi = x0 + (int32_t)(redo[k] / ny), yi = y0 + (int32_t)(redo[k] % ny);
+        px[k] = yi; py[k] = xi;
+        c->h_la[k] = (int32_t)(Y.off[yi + 1] - Y.off[yi]);
+        c->h_lb[k] = (int32_t)(X.off[xi + 1] - X.off[xi]);
+        rmr = std::max(rmr, c->h_la[k]); rmc = std::max(rmc, c->h_lb[k]);
+        cells += (long long)c->h_la[k] * c->h_lb[k];
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_redo.p, redo.data(), (size_t)nredo * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c->d_px.reserve((size_t)nredo, 1));
+    CUDA_TRY(c->d_py.reserve((size_t)nredo, 1));
+    CUDA_TRY(cudaMemcpyAsync(c->d_px.p, px.data(), (size_t)nredo * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_py.p, py.data(), (size_t)nredo * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                // the host vectors go out of scope below
+    CUDA_TRY(c->d_rscore.reserve((size_t)nredo, 1));
+    CUDA_TRY(c->d_rcounts.reserve((size_t)nredo * 4, 1));
+    CUDA_TRY(c->d_rmetrics.reserve((size_t)nredo * 4, 1));
+    AlignArgs b{};
+    fill_swapped(b, c);
+    b.px = c->d_px.p; b.py = c->d_py.p; b.ny = 1; b.npairs = (long long)nredo;
+    b.score = c->d_rscore.p; b.counts = c->d_rcounts.p; b.metrics = c->d_rmetrics.p;
+    c->cells += cells;
+    if ((rc = enqueue_align(c, b, rmr, rmc, false))) return rc;
+    scatter_redo_kernel<<<(unsigned)((nredo + 255) / 256), 256, 0, c->stream>>>(c->d_redo.p, (long long)nredo, nx, ny, c->d_rscore.p, c->d_rcounts.p,
+                                                                                  c->d_rmetrics.p, a.t_score, a.t_counts, a.t_metrics);
+    CUDA_TRY(cudaGetLastError());
+    c->last_kernel = 20;
+    return finish_align(c);
+}
+
+// Host-facing form: (x, y) results into out_* with a row stride of ld_xy pairs, (y, x) results into
+// tout_* with a row stride of ld_yx pairs (so a tile and its mirror can be written straight into
+// their places of one big matrix); walked in blocks of whole rows like taxi_align_rect.
+int taxi_align_rect_both(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
+                         int32_t* out_score, int32_t* out_counts, double* out_metrics, int64_t ld_xy,
+                         int32_t* tout_score, int32_t* tout_counts, double* tout_metrics, int64_t ld_yx)
+{
+    int rc = check_ctx(c, true);
+    if (rc) return rc;
+    reset_stats(c);
+    if ((rc = check_rect(c, x0, nx, y0, ny))) return rc;
+    if ((long long)nx * ny == 0) return TAXI_OK;
+    if (ld_xy < ny || ld_yx < nx) return fail(TAXI_E_ARG, "row strides smaller than the rows");
+    ON_DEVICE(c->device);
+    const int32_t rows = (int32_t)std::max<long long>(1, std::min<long long>(nx, kChunkPairs / ny));
+    const long long chunk = (long long)rows * ny;
+    if ((rc = reserve_outputs(c, 2 * chunk, flags))) return rc;     // second half: the mirrored block
+    int64_t redo_total = 0;
+    for (int32_t r0 = 0; r0 < nx; r0 += rows) {
+        const int32_t nr = std::min(rows, nx - r0);
+        const long long n = (long long)nr * ny;
+        int32_t* ds = c->d_score.p; int32_t* dc = c->d_counts.p; double* dm = c->d_metrics.p;
+        int32_t* ts = ds ? ds + chunk : nullptr; int32_t* tc = dc ? dc + 4 * chunk : nullptr; double* tm = dm ? dm + 4 * chunk : nullptr;
+        if ((rc = taxi_align_rect_both_device(c, x0 + r0, nr, y0, ny, flags, ds, dc, dm, ts, tc, tm))) return rc;
+        redo_total += c->last_redo;
+        auto copy2d = [&](void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
+            return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, c->stream);
+        };
+        if ((flags & TAXI_OUT_SCORE) && out_score) CUDA_TRY(copy2d(out_score + (size_t)r0 * ld_xy, ld_xy * 4, ds, (size_t)ny * 4, (size_t)ny * 4, nr));
+        if ((flags & TAXI_OUT_COUNTS) && out_counts) CUDA_TRY(copy2d(out_counts + 4 * (size_t)r0 * ld_xy, ld_xy * 16, dc, (size_t)ny * 16, (size_t)ny * 16, nr));
+        if ((flags & TAXI_OUT_METRICS) && out_metrics) CUDA_TRY(copy2d(out_metrics + 4 * (size_t)r0 * ld_xy, ld_xy * 32, dm, (size_t)ny * 32, (size_t)ny * 32, nr));
+        if ((flags & TAXI_OUT_SCORE) && tout_score) CUDA_TRY(copy2d(tout_score + r0, ld_yx * 4, ts, (size_t)nr * 4, (size_t)nr * 4, ny));
+        if ((flags & TAXI_OUT_COUNTS) && tout_counts) CUDA_TRY(copy2d(tout_counts + 4 * (size_t)r0, ld_yx * 16, tc, (size_t)nr * 16, (size_t)nr * 16, ny));
+        if ((flags & TAXI_OUT_METRICS) && tout_metrics) CUDA_TRY(copy2d(tout_metrics + 4 * (size_t)r0, ld_yx * 32, tm, (size_t)nr * 32, (size_t)nr * 32, ny));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        (void)n;
+    }
+    c->last_redo = redo_total;
     return TAXI_OK;
 }
 
@@ -1213,6 +1404,8 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
 }
 
 int taxi_last_kernel(taxi_ctx* c) { return c ? c->last_kernel : 0; }
+
+int64_t taxi_last_redo(taxi_ctx* c) { return c ? c->last_redo : 0; }
 
 int taxi_last_stats(taxi_ctx* c, int64_t* launches, int64_t* cells, double* kernel_ms)
 {

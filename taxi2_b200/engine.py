@@ -143,6 +143,50 @@ class Engine:
         N.check(self._lib.taxi_align_rect(self._ctx, x0, nx, y0, ny, flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, (nx, ny))
 
+    def align_rect_both(self, x0: int, nx: int, y0: int, ny: int, want=("score", "counts", "metrics"),
+                        out: dict | None = None, out_t: dict | None = None) -> tuple[dict, dict]:
+        """Both orientations of a rectangle -- (x, y) as (nx, ny, ...) arrays and (y, x) as (ny, nx, ...)
+        arrays -- from one alignment per unordered pair plus the re-alignment of the few
+        orientation-sensitive ones (taxi_align_rect_both).  Bit-identical to two align_rect calls with
+        the sets exchanged.  out / out_t: 2-D views (e.g. a tile and its mirror inside one matrix) whose
+        rows may be strided; the last axis must be contiguous."""
+        shapes = {"score": ((), np.int32), "counts": ((4,), np.int32), "metrics": ((4,), np.float64)}
+        flags = sum(f for k, f in (("score", N.OUT_SCORE), ("counts", N.OUT_COUNTS), ("metrics", N.OUT_METRICS)) if k in want)
+        res, res_t, ptr, ptr_t = {}, {}, {}, {}
+        ld = {"xy": None, "yx": None}
+        for key in ("score", "counts", "metrics"):
+            tail, dtype = shapes[key]
+            if key not in want:
+                ptr[key] = ptr_t[key] = None
+                continue
+            for which, given, store, ptrs, rows, cols in (("xy", out, res, ptr, nx, ny), ("yx", out_t, res_t, ptr_t, ny, nx)):
+                arr = given[key] if given is not None and key in given else np.empty((rows, cols, *tail), dtype=dtype)
+                if arr.shape != (rows, cols, *tail) or arr.dtype != np.dtype(dtype):
+                    raise ValueError(f"{key}: expected shape {(rows, cols, *tail)} {np.dtype(dtype)}")
+                item = arr.dtype.itemsize * (4 if tail else 1)
+                if arr.strides[1] != item or (tail and arr.strides[2] != arr.dtype.itemsize) or arr.strides[0] % item:
+                    raise ValueError(f"{key}: rows may be strided, pairs within a row must be contiguous")
+                stride = arr.strides[0] // item if rows > 1 else cols
+                if ld[which] not in (None, stride):
+                    raise ValueError("all outputs of one orientation must share their row stride (in pairs)")
+                ld[which] = stride
+                store[key] = arr
+                ptrs[key] = C.c_void_p(arr.ctypes.data)
+        N.check(self._lib.taxi_align_rect_both(self._ctx, x0, nx, y0, ny, flags, ptr["score"], ptr["counts"], ptr["metrics"], ld["xy"] or ny,
+                                               ptr_t["score"], ptr_t["counts"], ptr_t["metrics"], ld["yx"] or nx))
+        return res, res_t
+
+    @property
+    def last_redo(self) -> int:
+        """Pairs the last both-orientations call had to re-align the other way round."""
+        return int(self._lib.taxi_last_redo(self._ctx))
+
+    def align_rect_both_device(self, x0, nx, y0, ny, d_counts=0, d_metrics=0, t_counts=0, t_metrics=0) -> None:
+        """Device-resident form (pointers as ints); synchronous."""
+        flags = (N.OUT_COUNTS if d_counts else 0) | (N.OUT_METRICS if d_metrics else 0)
+        N.check(self._lib.taxi_align_rect_both_device(self._ctx, x0, nx, y0, ny, flags, None, C.c_void_p(d_counts), C.c_void_p(d_metrics),
+                                                      None, C.c_void_p(t_counts), C.c_void_p(t_metrics)))
+
     def align_rect_resident(self, x0: int, nx: int, y0: int, ny: int, want=("counts", "metrics")) -> None:
         """Same work with the results left in the library's device buffers (no download): what a
         caller that reduces on the device needs, and the device-resident leg of bench.py."""

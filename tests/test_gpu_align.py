@@ -670,3 +670,60 @@ def test_intra_task_kernel_for_few_long_pairs(engine):
         for k in (0, 5, 6):
             ox, oy, _ = oracle.align(xs[k], ys[k], scores)
             assert got[0][1][k].decode() == ox and got[0][2][k].decode() == oy
+
+
+@pytest.mark.parametrize("case", ["coi", "ties", "two_sets", "fallback_mixed", "fallback_scores"])
+def test_both_orientations_from_one_alignment(engine, case):
+    """versus_all.py:746 aligns (x, y) and (y, x).  taxi_align_rect_both derives the second from the
+    first wherever the traced path never had to choose between Ix and Iy at equal score, and
+    re-aligns the rest: bit-identical to aligning both ways, on barcodes (few sensitive pairs), on
+    two-letter low-complexity input (many), across two different sets, and on inputs that have to
+    fall back to two ordinary launches (mixed lengths, Needleman-Wunsch scores)."""
+    rng = np.random.default_rng({"coi": 1, "ties": 2, "two_sets": 3, "fallback_mixed": 4, "fallback_scores": 5}[case])
+    scores = (1, -1, -8, -1, -1, -1)
+    if case == "coi":
+        xs = coi_like(300, seed=11); ys = None
+    elif case == "ties":
+        xs, _ = random_pairs(rng, 150, 40, 160, sub=0.3, indel=0.1, alphabet=b"AT"); ys = None
+        scores = (1, -1, -2, -1, -1, -1)
+    elif case == "two_sets":
+        xs = coi_like(130, seed=12); ys = coi_like(90, length=600, seed=13)
+    elif case == "fallback_mixed":
+        xs, _ = random_pairs(rng, 60, 100, 1400, sub=0.1, indel=0.02); ys = None
+    else:
+        xs = coi_like(64, length=200, seed=14); ys = None
+        scores = (1, 0, 0, 0, 0, 0)
+    engine.set_scores(scores)
+    engine.load(xs, 0)
+    if ys is not None:
+        engine.load(ys, 1)
+    nx, ny = len(xs), len(ys if ys is not None else xs)
+    xy, yx = engine.align_rect_both(0, nx, 0, ny)
+    redo = engine.last_redo
+    want_xy = engine.align_rect(0, nx, 0, ny)
+    # the other orientation the ordinary way: the sets exchanged
+    engine.load(ys if ys is not None else xs, 0)
+    engine.load(xs, 1)
+    want_yx = engine.align_rect(0, ny, 0, nx)
+    for key in ("score", "counts"):
+        assert np.array_equal(xy[key], want_xy[key]), key
+        assert np.array_equal(yx[key], want_yx[key]), key
+    assert np.array_equal(xy["metrics"], want_xy["metrics"], equal_nan=True)
+    assert np.array_equal(yx["metrics"], want_yx["metrics"], equal_nan=True)
+    asymmetric = int((want_yx["counts"] != np.swapaxes(want_xy["counts"], 0, 1)).any(axis=2).sum())
+    if case in ("coi", "two_sets"):
+        assert 0 < redo < 0.05 * nx * ny and redo >= asymmetric          # a few per cent at most are re-aligned
+    if case == "ties":
+        assert redo >= asymmetric > 0
+    if case.startswith("fallback"):
+        assert redo == 0
+    # a tile and its mirror written straight into their places of one matrix (strided rows)
+    if ys is None and case == "coi":
+        engine.load(xs, 0)
+        big = {k: np.zeros((nx, nx, *t), dtype=d) for k, t, d in (("counts", (4,), np.int32), ("metrics", (4,), np.float64))}
+        r, c0 = slice(10, 110), slice(150, 290)
+        engine.align_rect_both(10, 100, 150, 140, want=("counts", "metrics"),
+                               out={k: v[r, c0] for k, v in big.items()}, out_t={k: v[c0, r] for k, v in big.items()})
+        assert np.array_equal(big["counts"][r, c0], want_xy["counts"][r, c0]) and np.array_equal(big["counts"][c0, r], want_xy["counts"][c0, r])
+        assert np.array_equal(big["metrics"][c0, r], want_xy["metrics"][c0, r], equal_nan=True)
+        assert not big["counts"][:10].any() and not big["counts"][110:150, :150].any()
