@@ -46,6 +46,14 @@ __device__ __forceinline__ uint32_t lop3_xor_or(uint32_t a, uint32_t b, uint32_t
     return r;
 }
 
+// bits of a where c is set, bits of b elsewhere: (0xF0 & 0xAA) | (0xCC & 0x55) = 0xE4
+__device__ __forceinline__ uint32_t lop3_mux(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t c)
 {
     uint32_t r;
@@ -98,7 +106,7 @@ struct Walk {
     int64_t wpos;                         // write cursor of the gapped strings
     int score;
     int tb, ca, cb;                       // the window element this lane holds: traceback code, x / y symbol codes
-    int nA0, nB0;                         // the end cell (SYM: the path starts there in the state that wins it)
+    bool entered;                         // SYM: the current cell was entered in its H state (start, or after a diagonal move)
 };
 
 // address of the traceback code of cell (ii, jj); MULTI = arena with several stripes
@@ -148,11 +156,11 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     if (SYM) {
         // Orientation.  The path of (y, x) is the transpose of this one unless the winner of H at a
         // cell the path enters is Ix with Iy at the same score (Biopython prefers Ix; transposed, the
-        // roles swap).  Bit 4 of a cell's code says so for that cell.  The path enters cells in their
-        // H state after a diagonal move (the cell behind the last visited one, lane V) and at the start.
-        const int behind = __shfl_sync(TAXI_FULL_MASK, tb, V & 31);
-        if (state == 0 && next == 1 && V < 32 && (behind & 16)) w.sens = true;
-        if (state == 1 && w.i == (int)w.nA0 && w.j == (int)w.nB0 && (__shfl_sync(TAXI_FULL_MASK, tb, 0) & 16)) w.sens = true;
+        // roles swap).  Bit 4 of a cell's code is CLEAR where Ix and Iy tie at that cell.  The path enters a cell in its H
+        // state at the start and after every diagonal move; if that state is Ix, the cell is the first
+        // one (lane 0) of the window this iteration looks at.
+        if (w.entered && state == 1 && !(__shfl_sync(TAXI_FULL_MASK, tb, 0) & 16)) w.sens = true;
+        w.entered = (state == 0);
     }
     const bool mine = lane < V;
     const unsigned visited = 0xffffffffu >> (32 - V);
@@ -257,7 +265,7 @@ __device__ __forceinline__ Walk walk_start(const AlignArgs& a, long long p, cons
     w.wpos = a.aln_x != nullptr ? a.aln_off[p + 1] : 0;
     w.score = ((int)(fin & 0xFFF0u) - bias) / 16 + beta * nA;
     w.tb = w.ca = w.cb = 0;
-    w.nA0 = nA; w.nB0 = nB;
+    w.entered = true;
     return w;
 }
 
@@ -417,7 +425,7 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
 // reproduces the leading end gap by itself (requires internal extend == end extend, checked on
 // the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
 // infinity".
-// SYM: every cell's code also says (bit 4) whether H was won by Ix with Iy at the same score -- the one
+// SYM: every cell's code also says (bit 4 clear) whether Ix and Iy hold the same score there -- the one
 // decision that differs when the pair is aligned the other way round; see walk_advance.
 template <int H, bool SYM = false>
 __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
@@ -512,10 +520,11 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                     const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
                     Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
                     if constexpr (SYM) {
-                        // H - Yt per half is 1 exactly when Ix won (tag 2) against Iy at the same score (tag 1);
-                        // min(., 2) * 16 puts that in bit 4 of the cleaned code (IADD + VIMNMX + IMAD + LOP3)
-                        const uint32_t tie16 = __vminu2(Hl[r] - Yt, 0x00020002u) * 16u;
-                        tc = lop3_and_or(tc, 0x000F000Fu, tie16);
+                        // Xt ^ Yt is 3 per half exactly where Ix and Iy hold the same score (tags 2 and 1), at
+                        // least 16 elsewhere: min(., 16) sets bit 4 where they do NOT tie, and one LOP3 takes
+                        // the low nibble from the code and the rest from that (LOP3 + VIMNMX + LOP3 per row pair)
+                        const uint32_t nt = __vminu2(Xt ^ Yt, 0x00100010u);
+                        tc = lop3_mux(tc, nt, 0x000F000Fu);
                     }
                     Xin = __viaddmax_u16x2(Mt, ncXM, Xt + cXX);
                     Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt + ((r == H - 1) ? cYYl : cYYi));

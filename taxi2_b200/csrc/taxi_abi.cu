@@ -963,6 +963,7 @@ int taxi_align_rect_both_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0,
     if (lo * 2 > mr && (rc = enqueue_align(c, a, mr, mc, true, true, true, &sym_used))) return rc;
     if (!sym_used) {
         // fallback: two ordinary launches, the second with the roles of the sets exchanged
+        c->last_redo = 0;
         if ((rc = taxi_align_rect_device(c, x0, nx, y0, ny, flags, d_score, d_counts, d_metrics))) return rc;
         if ((rc = finish_align(c))) return rc;
         AlignArgs b{};

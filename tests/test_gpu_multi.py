@@ -105,6 +105,34 @@ def test_best_matches_rows_and_column_tiles(single, devices, align):
                 assert np.array_equal(got["counts"], full["counts"][np.arange(len(queries)), want_idx])
 
 
+@pytest.mark.parametrize("devices", device_sets(), ids=lambda d: f"gpus{len(d)}x{len(set(d))}")
+def test_symmetric_matrix_equals_all_ordered_pairs(single, devices):
+    """versus_all.py:746 aligns (x, y) and (y, x).  align_matrix_symmetric aligns each unordered pair
+    once, mirrors the result and re-aligns the orientation-sensitive pairs: the full n x n matrices
+    must equal those of aligning every ordered pair, bit for bit -- barcodes (packed kernel with the
+    tie bit), block sizes that exercise the diagonal recursion and ragged edges, and a mixed-length
+    set that falls back to two launches per tile."""
+    from taxi2_b200.multi import MultiEngine
+
+    for name, seqs, blocks in (("coi", coi_like(700, seed=21), ((500, None), (128, 256), (2048, None))),
+                               ("mixed", mixed_sequences(), ((64, None),))):
+        single.set_scores(None)
+        single.load(seqs, 0)
+        want = single.align_rect(0, len(seqs), 0, len(seqs))
+        with MultiEngine(devices) as multi:
+            multi.load(seqs, 0)
+            for block, max_cols in blocks:
+                got = multi.align_matrix_symmetric(block=block, max_cols=max_cols, pinned=(block == 500))
+                for key in ("score", "counts"):
+                    assert np.array_equal(got[key], want[key]), (name, block, key)
+                assert np.array_equal(got["metrics"], want["metrics"], equal_nan=True), (name, block)
+                if name == "coi":
+                    asym = int((want["counts"] != np.swapaxes(want["counts"], 0, 1)).any(axis=2).sum()) // 2
+                    assert asym <= got["redo"] < 0.03 * len(seqs) ** 2 and got["cells"] < 0.7 * 650 * 650 * len(seqs) ** 2
+            rows = [(x0, nx) for x0, nx, _ in multi.iter_symmetric_rows(("metrics",), block=150)]
+            assert rows == [(x0, min(150, len(seqs) - x0)) for x0 in range(0, len(seqs), 150)]
+
+
 def test_best_rows_with_undefined_rows(single):
     single.load(["ACGTACGT", "NNNNNNNN", "ACGAACGT"], 0)
     single.load(["NNNNNNNN", "ACGTACGA", "ACGTACGT", "ACGTACGT"], 1)

@@ -63,17 +63,28 @@ def test_versus_all_outputs(tmp_path, align, write, multiply, native):
     assert_same_tree(task.work_dir, want)
 
 
-def test_versus_all_on_the_50_sequence_sample(tmp_path):
+@pytest.mark.parametrize("write,block_pairs", [(True, None), (False, None), (False, 600)])
+def test_versus_all_on_the_50_sequence_sample(tmp_path, monkeypatch, write, block_pairs):
     """The reference's Taxi2test1_50.tab as shipped (2 500 ordered pairs, 416-618 bp, species and
-    genera from the organism column): all output files, aligned pairs included, byte for byte."""
+    genera from the organism column): all output files, aligned pairs included, byte for byte.
+    Without the aligned-pairs file the task aligns each unordered pair once and mirrors the result
+    (MultiEngine.iter_symmetric_rows), in one block and in blocks of 12 rows."""
+    from taxi2_b200.tasks import common
+
+    if block_pairs:
+        monkeypatch.setattr(common, "MAX_BLOCK_PAIRS", block_pairs)
     seqs, species, genera = load("Taxi2test1_50.tab")
     task = VersusAll()
     task.work_dir = tmp_path / "got"
     task.progress_handler = SILENT
     task.input.sequences = seqs
     task.input.species, task.input.genera = species, genera
+    task.params.pairs.write = write
     task.start()
     ref_pipeline.versus_all(list(seqs), tmp_path / "want", species, genera)
+    if not write:
+        (tmp_path / "want" / "align" / "aligned_pairs.txt").unlink()
+        (tmp_path / "want" / "align").rmdir()
     assert_same_tree(task.work_dir, tmp_path / "want")
 
 

@@ -21,8 +21,9 @@ for line in sass.splitlines():
         functions[name].append(line)
 
 TARGETS = [  # (mangled-name fragment, signature instruction, minimum count in the loop, output name, note)
-    ("gotoh_pair16_kernelILi21ELi1E", "VIMNMX3.U16x2", 21, "gotoh_pair16_21_1", "one column step of 21 row slots x 2 pairs per lane (42 cells per lane)"),
-    ("gotoh_pair16_kernelILi21ELi2E", "VIMNMX3.U16x2", 21, "gotoh_pair16_21_2", "multi-stripe variant, one column step"),
+    ("gotoh_pair16_kernelILi21ELi1ELb0E", "VIMNMX3.U16x2", 21, "gotoh_pair16_21_1", "one column step of 21 row slots x 2 pairs per lane (42 cells per lane)"),
+    ("gotoh_pair16_kernelILi21ELi1ELb1E", "VIMNMX3.U16x2", 21, "gotoh_pair16_21_1_sym", "both-orientations variant (Ix / Iy tie bit per cell), one column step"),
+    ("gotoh_pair16_kernelILi21ELi2ELb0E", "VIMNMX3.U16x2", 21, "gotoh_pair16_21_2", "multi-stripe variant, one column step"),
     ("gotoh_warp_kernelILi21E", "VIMNMX3", 21, "gotoh_warp_21", "general int32 kernel, one column step of 21 rows per lane"),
     ("count_rect_kernel", "POPC", 40, "count_rect", "popcount kernel: 4 x rows x 5 words per iteration (20 word pairs)"),
     ("count_tc_kernel", "UTCIMMA", 4, "count_tc_mma", "tensor-core kernel: the MMA issue loop (4 UTCIMMA per 128-byte k-block)"),
