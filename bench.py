@@ -19,6 +19,9 @@ Prints ONE JSON line (rank 0):
   strong    (C3) one FIXED job -- 8192 x 16384 pairs of the C3 matrix -- sharded over all N GPUs by
             the product path (taxi2_b200/multi.py: one process, one thread per GPU, static LPT
             tiles, every GPU's D2H landing in its slice of one pinned host matrix), gather included
+  versus_all (C3) versusAll of the first 8192 sequences as a whole job: all 6.7e7 ORDERED pairs delivered
+            into one pinned host matrix from one alignment per unordered pair (mirrored; orientation-
+            sensitive pairs re-aligned), checked against the ordinary path on a band of rows
 `--impl reference` times the CPU restatement of the reference path (oracle/, "port": Biopython
 and the Rust distance crate are not installable here) on all host threads, on the same tiles.
 """
@@ -44,6 +47,7 @@ SEQ_LEN = 650
 TILE_X = 1536
 TILE_Y = 2048
 STRONG_X, STRONG_Y = 8192, 16384
+SYM_N = 8192               # versusAll as a whole job: all ordered pairs of the first SYM_N sequences
 OPS_PER_CELL = 13          # scalar INT32 ops of the score-only 3-state recurrence
 SCORES_TEXT = "match 1, mismatch -1, internal open -8 / extend -1, end open -1 / extend -1"
 
@@ -469,6 +473,15 @@ def run_c3(args, rank: int, local_rank: int, world: int) -> None:
         if distributed:
             dist.barrier(group=host_group)
 
+    # ---- versusAll as a whole: both orientations from one alignment per unordered pair -------------
+    versus_all = None
+    if args.strong and n >= SYM_N:
+        if rank == 0:
+            versus_all = versus_all_symmetric(data, off, world)
+            torch.cuda.set_device(local_rank)
+        if distributed:
+            dist.barrier(group=host_group)
+
     # ---- aggregate over ranks (max time, sum work) ----------------------------------------------
     if distributed:
         t = torch.tensor([dt, dt_e2e, kernel_ms], dtype=torch.float64, device="cuda")
@@ -505,7 +518,7 @@ def run_c3(args, rank: int, local_rank: int, world: int) -> None:
                               sample=f"{cpu['pairs']} random ordered pairs of the first timed {TILE_X}x{TILE_Y} tile in {cpu['seconds']:.1f} s"),
             e2e=dict(value=npairs * args.steps * world / dt_e2e, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      steps=args.steps),
-            strong=strong,
+            strong=strong, versus_all=versus_all,
             gpu_launches=launches + e2e_launches * world, clocks=clk, checksum=checksum,
         )
         print(json.dumps(line), flush=True)
@@ -544,6 +557,43 @@ def strong_scaling(data, off, world: int, debug: bool) -> dict:
             n_gpus=world, pairs=pairs, seconds=dt, value=pairs / dt, unit="pairs/s", gcups=res["cells"] / dt / 1e9,
             tiles=res["tiles"], kernel_seconds_sum=res["kernel_ms"] / 1e3, gather="host (pinned), inside the timed region; no collective",
             checksum=int(res["counts"][::97, ::89].sum()))
+    finally:
+        multi.close()
+
+
+def versus_all_symmetric(data, off, world: int) -> dict:
+    """versusAll on the first SYM_N sequences of C3 as a whole job on all `world` GPUs: every ORDERED pair's
+    counts and metrics in one page-locked n x n host matrix (versus_all.py:746 aligns (x, y) and (y, x)),
+    from ONE alignment per unordered pair -- the kernel notes on the traced path whether the other
+    orientation could align differently (a tie between a vertical and a horizontal gap), those pairs
+    are re-aligned, the rest mirrored (MultiEngine.align_matrix_symmetric).  `value` counts ordered pairs
+    DELIVERED per second; `alignments` is what was actually aligned.  A band of rows is checked
+    against the ordinary one-alignment-per-ordered-pair path inside the run."""
+    from taxi2_b200.engine import PinnedArray
+    from taxi2_b200.multi import MultiEngine
+
+    multi = MultiEngine(list(range(world)))
+    try:
+        multi.load((data[: off[SYM_N]], off[: SYM_N + 1]), 0)
+        counts = PinnedArray((SYM_N, SYM_N, 4), np.int32)
+        metrics = PinnedArray((SYM_N, SYM_N, 4), np.float64)
+        out = dict(counts=counts.array, metrics=metrics.array)
+        band = multi.align_matrix(want=("counts", "metrics"), x_range=(SYM_N // 2, SYM_N // 2 + 64 * world))   # also the warm-up
+        t0 = time.perf_counter()
+        res = multi.align_matrix_symmetric(want=("counts", "metrics"), out=out)
+        dt = time.perf_counter() - t0
+        rows = slice(SYM_N // 2, SYM_N // 2 + 64 * world)
+        same = bool(np.array_equal(band["counts"], res["counts"][rows]) and
+                    np.array_equal(band["metrics"].view(np.int64), res["metrics"][rows].view(np.int64)))
+        pairs = SYM_N * SYM_N
+        lens = np.diff(off[: SYM_N + 1])
+        return dict(
+            job=f"versusAll of {SYM_N} C3 sequences: {pairs} ordered pairs, counts + 4 metrics in one pinned host matrix "
+                f"({(counts.nbytes + metrics.nbytes) / 1e9:.1f} GB), one alignment per unordered pair + re-alignment of the orientation-sensitive ones",
+            n_gpus=world, ordered_pairs=pairs, seconds=dt, value=pairs / dt, unit="ordered pairs/s delivered",
+            alignments=int(round(res["cells"] / float(lens.mean()) ** 2)), realigned=int(res["redo"]), gcups_computed=res["cells"] / dt / 1e9,
+            tiles=res["tiles"], kernel_seconds_sum=res["kernel_ms"] / 1e3,
+            identical_to_ordered_path=same, rows_checked=64 * world, checksum=int(res["counts"][::97, ::89].sum()))
     finally:
         multi.close()
 

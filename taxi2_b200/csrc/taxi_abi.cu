@@ -1010,7 +1010,7 @@ int taxi_align_rect_both_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0,
     b.px = c->d_px.p; b.py = c->d_py.p; b.ny = 1; b.npairs = (long long)nredo;
     b.score = c->d_rscore.p; b.counts = c->d_rcounts.p; b.metrics = c->d_rmetrics.p;
     c->cells += cells;
-    if ((rc = enqueue_align(c, b, rmr, rmc, false))) return rc;
+    if ((rc = enqueue_align(c, b, rmr, rmc))) return rc;
     scatter_redo_kernel<<<(unsigned)((nredo + 255) / 256), 256, 0, c->stream>>>(c->d_redo.p, (long long)nredo, nx, ny, c->d_rscore.p, c->d_rcounts.p,
                                                                                   c->d_rmetrics.p, a.t_score, a.t_counts, a.t_metrics);
     CUDA_TRY(cudaGetLastError());
