@@ -230,14 +230,24 @@ class MultiEngine:
         return self._matrix("count", want, rows_per_tile, pinned, x_range, out)
 
     # -- versusAll: both orientations from one alignment per unordered pair ---------------------------
-    def symmetric_tiles(self, block: int, max_cols: int | None = None) -> list[Tile]:
+    def symmetric_tiles(self, block: int | None = None, max_cols: int | None = None) -> list[Tile]:
         """Tiles of the UPPER triangle of set 0 x set 0 in row-block-major order: per block of rows its
         diagonal square, then rectangles of at most max_cols columns to the right of it.  A
-        rectangle (rows r, columns c) yields the results of (r, c) and, mirrored, of (c, r)."""
+        rectangle (rows r, columns c) yields the results of (r, c) and, mirrored, of (c, r).
+        block=None: 2048-row blocks with wide rectangles on one GPU; with several GPUs square tiles,
+        small enough that every GPU gets half a dozen of them for the LPT plan to balance."""
         lens = self.lens[0]
         if lens is None:
             raise ValueError("no sequences loaded")
         n = len(lens)
+        gpus = len(self.engines)
+        if block is None:
+            blocks = -(-n // 2048)
+            if gpus > 1:
+                blocks = max(blocks, int(np.ceil(np.sqrt(12.0 * gpus))) + 1)
+            block = -(-n // max(1, blocks))
+            if max_cols is None and gpus > 1:
+                max_cols = block
         block = max(1, int(block))
         max_cols = max(block, int(max_cols or 4 * block))
         cum = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
@@ -267,7 +277,7 @@ class MultiEngine:
         self._diagonal_block(engine, x0, h, want, out, acc)
         self._diagonal_block(engine, x0 + h, n - h, want, out, acc)
 
-    def iter_symmetric_rows(self, want=("score", "counts", "metrics"), block: int = 2048, max_cols: int | None = None,
+    def iter_symmetric_rows(self, want=("score", "counts", "metrics"), block: int | None = None, max_cols: int | None = None,
                             pinned: bool = False, out: dict | None = None, on_diagonal=None) -> Iterator[tuple[int, int, dict]]:
         """All ordered pairs of set 0 x set 0 (versus_all.py:746) with ONE alignment per unordered pair:
         the alignment of (y, x) is the transpose of that of (x, y) unless a tie between a vertical and
@@ -325,7 +335,7 @@ class MultiEngine:
                 res.update(acc, tiles=len(tiles))
                 yield tile.x0, tile.nx, res
 
-    def align_matrix_symmetric(self, want=("score", "counts", "metrics"), block: int = 2048, max_cols: int | None = None,
+    def align_matrix_symmetric(self, want=("score", "counts", "metrics"), block: int | None = None, max_cols: int | None = None,
                                pinned: bool = False, out: dict | None = None) -> dict:
         """align_matrix for set 0 x set 0 at roughly 0.6 of its cost (iter_symmetric_rows)."""
         res = None

@@ -114,7 +114,7 @@ def test_symmetric_matrix_equals_all_ordered_pairs(single, devices):
     set that falls back to two launches per tile."""
     from taxi2_b200.multi import MultiEngine
 
-    for name, seqs, blocks in (("coi", coi_like(700, seed=21), ((500, None), (128, 256), (2048, None))),
+    for name, seqs, blocks in (("coi", coi_like(700, seed=21), ((500, None), (128, 256), (None, None))),
                                ("mixed", mixed_sequences(), ((64, None),))):
         single.set_scores(None)
         single.load(seqs, 0)

@@ -148,3 +148,31 @@ def test_combine_best_is_the_first_minimum_in_reference_order():
         assert np.array_equal(best[ok], d[np.arange(nx)[ok], want[ok]], equal_nan=True)
         assert np.array_equal(cnt[ok], counts[np.arange(nx)[ok], want[ok]])
         assert np.isnan(best[~ok]).all()
+
+
+@pytest.mark.parametrize("gpus,n,block,max_cols", [(1, 37, 8, None), (3, 101, None, None), (2, 64, 16, 16), (4, 5, 2048, None), (1, 1, None, None)])
+def test_symmetric_tiles_cover_every_unordered_pair_once(gpus, n, block, max_cols):
+    """The upper-triangle tiling behind versusAll's one-alignment-per-unordered-pair route: diagonal
+    squares plus rectangles strictly to their right cover each unordered pair exactly once, in
+    row-block-major order, and the symmetric matrix assembled from oracle-backed engines equals the
+    matrix of every ordered pair."""
+    from fake_engine import oracle_multi
+
+    rng = np.random.default_rng(n)
+    seqs = ["".join(rng.choice(list("ACGT"), size=int(rng.integers(5, 12)))) for _ in range(n)]
+    multi = oracle_multi(gpus)
+    multi.load(seqs, 0)
+    tiles = multi.symmetric_tiles(block, max_cols)
+    seen = np.zeros((n, n), dtype=np.int32)
+    for t in tiles:
+        assert t.y0 >= t.x0 and (t.y0 == t.x0 and t.nx == t.ny or t.y0 >= t.x0 + t.nx)
+        seen[t.x0:t.x0 + t.nx, t.y0:t.y0 + t.ny] += 1
+        if t.y0 != t.x0:
+            seen[t.y0:t.y0 + t.ny, t.x0:t.x0 + t.nx] += 1      # the mirror image the rectangle fills as well
+    assert (seen == 1).all()
+    assert [t.index for t in tiles] == list(range(len(tiles))) and [t.x0 for t in tiles] == sorted(t.x0 for t in tiles)
+    want = multi.align_matrix()
+    got = multi.align_matrix_symmetric(block=block, max_cols=max_cols)
+    for key in ("score", "counts"):
+        assert np.array_equal(got[key], want[key])
+    assert np.array_equal(got["metrics"], want["metrics"], equal_nan=True)
