@@ -171,7 +171,7 @@ def test_symmetric_tiles_cover_every_unordered_pair_once(gpus, n, block, max_col
             seen[t.y0:t.y0 + t.ny, t.x0:t.x0 + t.nx] += 1      # the mirror image the rectangle fills as well
     assert (seen == 1).all()
     assert [t.index for t in tiles] == list(range(len(tiles))) and [t.x0 for t in tiles] == sorted(t.x0 for t in tiles)
-    want = multi.align_matrix()
+    want = multi.engines[0].align_rect(0, n, 0, n)
     got = multi.align_matrix_symmetric(block=block, max_cols=max_cols)
     for key in ("score", "counts"):
         assert np.array_equal(got[key], want[key])
