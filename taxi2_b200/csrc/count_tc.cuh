@@ -30,11 +30,12 @@
 // subtracted in the epilogue exactly as in the popcount kernel (gaps_outside_trim on the planes),
 // and the fp64 metrics are computed there too, so the kernel writes the same 16 B + 32 B per pair.
 //
-// One CTA of 32 warps per tile, one CTA per SM (the four accumulators take all 512 TMEM columns).
+// One CTA per tile of 128 y columns x TX x rows (TcGeom: 32 warps and all 512 TMEM columns for TX = 128,
+// 16 warps and half of them for TX = 64, two CTAs per SM).
 // The y tile is the A operand, so a TMEM lane -- an epilogue thread -- is a y column and the 32
 // threads of a warp write 32 consecutive pairs of one x row: the same coalesced 16 B + 32 B per pair
 // as the popcount kernel.  Lane 0 of warp 0 feeds TMA, lane 0 of warp 1 issues the MMAs, then all
-// 32 warps (4 TMEM lane quarters x 8 groups of 16 x rows) do trim, metrics and stores -- the
+// warps (4 TMEM lane quarters x TX / 16 groups of 16 x rows) do trim, metrics and stores -- the
 // epilogue, not the contraction, is what bounds the kernel.
 #pragma once
 #include <cuda.h>
@@ -45,10 +46,18 @@ namespace taxi {
 
 constexpr int TC_TILE = 128;              // pairs per tile side; also bytes of K per pipeline stage
 constexpr int TC_UMMA_K = 32;             // bytes of K per tcgen05.mma (8-bit operands)
-constexpr int TC_STAGES = 5;
-constexpr int TC_THREADS = 1024;
 constexpr int TC_ROW_SEGMENTS = 8;        // row length in units of Lp
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * 2 * TC_TILE * TC_TILE + 1024;
+// Tile geometry: TC_TILE y columns (TMEM lanes) x TX x rows (TMEM columns per accumulator).  TX = 128: one
+// CTA of 32 warps per SM, the four accumulators fill the 512 TMEM columns.  TX = 64: CTAs of 16 warps, two per
+// SM (256 TMEM columns and 97 KB of shared memory each), so one CTA's contraction runs under the other's epilogue.
+template <int TX> struct TcGeom {
+    static constexpr int THREADS = TX * 8;                          // 16 x rows per warp and TMEM lane quarter
+    static constexpr int STAGES = TX == 128 ? 5 : 4;
+    static constexpr int STAGE_X = TX * TC_TILE, STAGE_Y = TC_TILE * TC_TILE;
+    static constexpr size_t SMEM = (size_t)STAGES * (STAGE_X + STAGE_Y) + 1024;
+    static constexpr int TMEM_COLS = 4 * TX;
+    static constexpr int CTAS_PER_SM = TX == 128 ? 1 : 2;
+};
 
 // one thread per (sequence, 4 columns): planes -> operand row
 __global__ void tc_operands_kernel(const uint4* __restrict__ planes, int32_t nseq, int32_t W, int32_t Lp, int8_t* __restrict__ out)
@@ -142,21 +151,23 @@ struct CountTcArgs {
     int32_t LpX, LpY;     // padded columns of each set's operand rows (segment offsets)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int TX>
+__global__ void __launch_bounds__(TcGeom<TX>::THREADS, TcGeom<TX>::CTAS_PER_SM)
 count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const CountTcArgs args)
 {
     using namespace tc;
+    using G = TcGeom<TX>;
+    constexpr int TC_STAGES = G::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int STAGE_BYTES = TC_TILE * TC_TILE;                   // one operand tile: 128 rows x 128 bytes
-    uint8_t* sX = smem;
-    uint8_t* sY = smem + TC_STAGES * STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sY + TC_STAGES * STAGE_BYTES);
+    uint8_t* sY = smem;                                              // operand tiles: rows of 128 bytes (TC_TILE y rows, TX x rows)
+    uint8_t* sX = smem + TC_STAGES * G::STAGE_Y;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sX + TC_STAGES * G::STAGE_X);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* accum_full = empty + TC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
     const CountArgs& a = args.c;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xt = blockIdx.y * TC_TILE, yt = blockIdx.x * TC_TILE;   // tile origin inside the rectangle
+    const int xt = blockIdx.y * TX, yt = blockIdx.x * TC_TILE;   // tile origin inside the rectangle
     const int Lp = args.Lp;
     const int blocks_per_L = Lp / TC_TILE;
     const int kblocks = 6 * blocks_per_L;
@@ -171,7 +182,7 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -197,13 +208,13 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             int acc, kx, ky;
             segment(kb, acc, kx, ky);
             mbar_wait(empty + s, ((kb / TC_STAGES) & 1) ^ 1);
-            mbar_expect_tx(full + s, 2 * STAGE_BYTES);
-            tma_load_2d(sX + s * STAGE_BYTES, &map_x, full + s, kx, a.x0 + xt);
-            tma_load_2d(sY + s * STAGE_BYTES, &map_y, full + s, ky, a.y0 + yt);
+            mbar_expect_tx(full + s, G::STAGE_X + G::STAGE_Y);
+            tma_load_2d(sX + s * G::STAGE_X, &map_x, full + s, kx, a.x0 + xt);
+            tma_load_2d(sY + s * G::STAGE_Y, &map_y, full + s, ky, a.y0 + yt);
         }
     } else if (warp == 1 && lane == 0) {
-        // S32 accumulators, signed 8-bit A and B, both K-major, N = 128, M = 128; A = the y tile (TMEM lanes), B = the x tile
-        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+        // S32 accumulators, signed 8-bit A and B, both K-major, N = TX, M = 128; A = the y tile (TMEM lanes), B = the x tile
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TX >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
         int prev_acc = -1;
         for (int kb = 0; kb < kblocks; ++kb) {
             const int s = kb % TC_STAGES;
@@ -213,8 +224,8 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < TC_TILE / TC_UMMA_K; ++k)
-                umma_i8(tmem + (uint32_t)(acc * TC_TILE), umma_desc(sY + s * STAGE_BYTES, k * TC_UMMA_K),
-                        umma_desc(sX + s * STAGE_BYTES, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
+                umma_i8(tmem + (uint32_t)(acc * TX), umma_desc(sY + s * G::STAGE_Y, k * TC_UMMA_K),
+                        umma_desc(sX + s * G::STAGE_X, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
             prev_acc = acc;
             umma_commit(empty + s);
         }
@@ -237,10 +248,10 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int ch = 0; ch < 2; ++ch) {
             const int r0 = cg * 16 + ch * 8;
             int A0[8], A1[8], A2[8], A3[8];
-            tmem_ld8(lane_addr + (uint32_t)(0 * TC_TILE + r0), A0);
-            tmem_ld8(lane_addr + (uint32_t)(1 * TC_TILE + r0), A1);
-            tmem_ld8(lane_addr + (uint32_t)(2 * TC_TILE + r0), A2);
-            tmem_ld8(lane_addr + (uint32_t)(3 * TC_TILE + r0), A3);
+            tmem_ld8(lane_addr + (uint32_t)(0 * TX + r0), A0);
+            tmem_ld8(lane_addr + (uint32_t)(1 * TX + r0), A1);
+            tmem_ld8(lane_addr + (uint32_t)(2 * TX + r0), A2);
+            tmem_ld8(lane_addr + (uint32_t)(3 * TX + r0), A3);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -261,7 +272,7 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(G::TMEM_COLS));
 }
 
 }  // namespace taxi

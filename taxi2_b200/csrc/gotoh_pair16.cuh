@@ -241,9 +241,11 @@ __device__ __forceinline__ void walk_finish(Walk& w, const AlignArgs& a, int lan
         // path was orientation-sensitive, in which case the host re-aligns (y, x) on its own
         if (w.sens) {
             const unsigned long long k = atomicAdd(a.redo_count, 1ULL);
+            TAXI_CHECK(a, k < (unsigned long long)a.npairs, 4);
             a.redo[k] = w.p;
         } else {
             const long long t = (w.p % a.ny) * (long long)a.nx + w.p / a.ny;
+            TAXI_CHECK(a, t >= 0 && t < a.npairs && w.p / a.ny < a.nx, 5);
             if (a.t_score) a.t_score[t] = w.score;
             if (a.t_counts) *reinterpret_cast<int4*>(a.t_counts + 4 * t) = make_int4(same, ts, tv, w.gapc);
             if (a.t_metrics) {

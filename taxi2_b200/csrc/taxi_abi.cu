@@ -92,7 +92,8 @@ struct SeqSet {
     DevBuf<int8_t> tcops;           // [n][8 * Lp]
     int32_t Lp = 0;                 // columns padded to TC_TILE
     bool tc_built = false;
-    CUtensorMap tc_map;
+    CUtensorMap tc_map;            // boxes of 128 rows
+    CUtensorMap tc_map64;          // boxes of 64 rows (x role of the two-CTAs-per-SM geometry)
     int32_t W = 0;
 };
 
@@ -117,6 +118,7 @@ struct taxi_ctx {
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
     int no_coop = 0;                // option: never use the intra-task kernel for long pairs
+    int tc_tile_x = 64;             // option: x rows per tile of the tensor-core counting kernel (128: one CTA per SM, 64: two)
     int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch
@@ -1187,11 +1189,15 @@ int ensure_tc_operands(taxi_ctx* c, SeqSet& s)
     }
     cuuint64_t dims[2] = {(cuuint64_t)row, (cuuint64_t)std::max(s.n, 1)};
     cuuint64_t strides[1] = {(cuuint64_t)row};
-    cuuint32_t box[2] = {(cuuint32_t)TC_TILE, (cuuint32_t)TC_TILE};
     cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(&s.tc_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.tcops.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(TAXI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    // boxes of 128 bytes of K x 128 rows (the y role, and the x role of the one-CTA-per-SM geometry) or 64 rows (x role, two CTAs per SM)
+    for (int half = 0; half < 2; ++half) {
+        cuuint32_t box[2] = {(cuuint32_t)TC_TILE, (cuuint32_t)(half ? TC_TILE / 2 : TC_TILE)};
+        const CUresult r = encode(half ? &s.tc_map64 : &s.tc_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s.tcops.p, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(TAXI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
     s.tc_built = true;
     return TAXI_OK;
 }
@@ -1217,7 +1223,7 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
     if (c->count_kernel != 1) {
         const long long tiles = (long long)((a.nx + TC_TILE - 1) / TC_TILE) * ((a.ny + TC_TILE - 1) / TC_TILE);
         const bool fits = tc_operand_bytes(X) <= kTcMaxOperandBytes && tc_operand_bytes(Y) <= kTcMaxOperandBytes &&
-                          (a.nx + TC_TILE - 1) / TC_TILE <= 65535;
+                          (a.nx + 63) / 64 <= 65535;
         if (fits && (c->count_kernel == 2 || tiles >= 2LL * c->sms)) {
             int rc = ensure_tc_operands(c, c->set[0]);
             if (rc == TAXI_OK && c->set[1].loaded) rc = ensure_tc_operands(c, c->set[1]);
@@ -1226,10 +1232,14 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
             const SeqSet& YY = yset(c);
             a.slab = 0;
             CountTcArgs t{a, std::min(XX.Lp, YY.Lp), XX.Lp, YY.Lp};
-            CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-            dim3 grid((unsigned)((a.ny + TC_TILE - 1) / TC_TILE), (unsigned)((a.nx + TC_TILE - 1) / TC_TILE));
+            const bool wide = c->tc_tile_x == 128;
+            const int tx = wide ? 128 : 64;
+            dim3 grid((unsigned)((a.ny + TC_TILE - 1) / TC_TILE), (unsigned)((a.nx + tx - 1) / tx));
+            if (wide) CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcGeom<128>::SMEM));
+            else CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcGeom<64>::SMEM));
             CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-            count_tc_kernel<<<grid, TC_THREADS, TC_SMEM, c->stream>>>(XX.tc_map, YY.tc_map, t);
+            if (wide) count_tc_kernel<128><<<grid, TcGeom<128>::THREADS, TcGeom<128>::SMEM, c->stream>>>(XX.tc_map, YY.tc_map, t);
+            else count_tc_kernel<64><<<grid, TcGeom<64>::THREADS, TcGeom<64>::SMEM, c->stream>>>(XX.tc_map64, YY.tc_map, t);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
             c->launches += 1;
@@ -1400,6 +1410,11 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
     if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
     if (std::strcmp(key, "count_kernel") == 0) { c->count_kernel = value; return TAXI_OK; }
+    if (std::strcmp(key, "tc_tile_x") == 0) {
+        if (value != 64 && value != 128) return fail(TAXI_E_ARG, "tc_tile_x must be 64 or 128");
+        c->tc_tile_x = value;
+        return TAXI_OK;
+    }
     if (std::strcmp(key, "no_coop") == 0) { c->no_coop = value; return TAXI_OK; }
     return fail(TAXI_E_ARG, "unknown option %s", key);
 }

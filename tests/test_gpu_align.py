@@ -615,19 +615,23 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
     cols = ys if ys is not None else xs
     nx, ny = len(xs), len(cols)
     results = {}
-    for kernel in (1, 2):
+    for kernel, tile_x in ((1, 64), (2, 64), (2, 128)):   # popcount; tensor cores with two CTAs per SM, with one
         engine.set_option("count_kernel", kernel)
+        engine.set_option("tc_tile_x", tile_x)
         try:
             full = engine.count_rect(0, nx, 0, ny)
             assert engine.last_kernel == (8 if kernel == 1 else 9)
             part = engine.count_rect(37, nx - 50, 11, ny - 29)
         finally:
             engine.set_option("count_kernel", 0)
-        results[kernel] = full
+            engine.set_option("tc_tile_x", 64)
+        results[kernel, tile_x] = full
         assert np.array_equal(part["counts"], full["counts"][37:nx - 13, 11:ny - 18])
         assert np.array_equal(part["metrics"], full["metrics"][37:nx - 13, 11:ny - 18], equal_nan=True)
-    assert np.array_equal(results[1]["counts"], results[2]["counts"])
-    assert np.array_equal(results[1]["metrics"], results[2]["metrics"], equal_nan=True)
+    for tile_x in (64, 128):
+        assert np.array_equal(results[1, 64]["counts"], results[2, tile_x]["counts"]), tile_x
+        assert np.array_equal(results[1, 64]["metrics"], results[2, tile_x]["metrics"], equal_nan=True), tile_x
+    results[2] = results[2, 64]
     data, off = pack_strings(xs + (ys or []))
     px = rng.integers(0, nx, 3000).astype(np.int32)
     py = rng.integers(0, ny, 3000).astype(np.int32)

@@ -29,6 +29,12 @@ def rect(n, length, **options):
 
 
 rect(384, 650)
+# both orientations of a 384 x 384 rectangle of two different row ranges: the SYM variant (tie bit per cell) + the re-alignment launch
+eng.load(coi_like(768, length=650, seed=650), 0)
+tc_ = torch.empty((384 * 384, 4), dtype=torch.int32, device="cuda"); tm_ = torch.empty((384 * 384, 4), dtype=torch.float64, device="cuda")
+uc_ = torch.empty_like(tc_); um_ = torch.empty_like(tm_)
+eng.align_rect_both_device(0, 384, 384, 384, tc_.data_ptr(), tm_.data_ptr(), uc_.data_ptr(), um_.data_ptr())
+print("both orientations 384 x 384: kernel", eng.last_kernel, "re-aligned", eng.last_redo)
 rect(256, 1200)
 rect(256, 650, force_general=1)
 # alignment-free rectangle at BASELINE C2 size: 9000 pre-aligned rows x 618 columns, one launch
@@ -40,9 +46,10 @@ n = len(off) - 1
 eng.load((data, off), 0)
 c = torch.empty((n * n, 4), dtype=torch.int32, device="cuda")
 m = torch.empty((n * n, 4), dtype=torch.float64, device="cuda")
-for kernel in (1, 2, 2):   # popcount kernel, then the tensor-core kernel twice (the first launch builds its operands)
+for kernel, tile_x in ((1, 128), (2, 128), (2, 128), (2, 64)):   # popcount kernel, then the tensor-core kernel (the first launch builds its operands); last: two CTAs per SM
     eng.set_option("count_kernel", kernel)
+    eng.set_option("tc_tile_x", tile_x)
     before = eng.stats()["kernel_ms"]
     eng.count_rect_device(0, n, 0, n, c.data_ptr(), m.data_ptr())
     eng.sync()
-    print("count", {1: "popcount", 2: "tensor cores"}[kernel], n, "x", n, "ms", round(eng.stats()["kernel_ms"] - before, 3))
+    print("count", {1: "popcount", 2: f"tensor cores (x tile {tile_x})"}[kernel], n, "x", n, "ms", round(eng.stats()["kernel_ms"] - before, 3))

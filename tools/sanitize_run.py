@@ -57,5 +57,14 @@ eng.count_pairs(np.arange(300, dtype=np.int32), np.arange(300, dtype=np.int32)[:
 eng.best_rows(0, 300, 0, 300, 0, align=False)
 eng.load(seqs[:8], 0); eng.load(seqs[8:20], 1)
 eng.best_rows(0, 8, 0, 12, 0, align=True)
+eng.load(seqs, 0)
+eng.align_rect_both(0, 10, 10, 14)
+note(f"both orientations 10x14 (re-aligned: {eng.last_redo})")
+for tile_x in (128, 64):
+    eng.set_option("count_kernel", 2); eng.set_option("tc_tile_x", tile_x)
+    eng.load(rows, 0)
+    eng.count_rect(0, 300, 0, 300)
+    note(f"tensor-core counting kernel, x tile {tile_x}")
+eng.set_option("count_kernel", 0)
 print("kernels:", kernels)
 print("sanitize_run ok")
