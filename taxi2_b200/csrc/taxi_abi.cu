@@ -118,7 +118,7 @@ struct taxi_ctx {
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
     int no_coop = 0;                // option: never use the intra-task kernel for long pairs
-    int tc_tile_x = 64;             // option: x rows per tile of the tensor-core counting kernel (128: one CTA per SM, 64: two)
+    int tc_tile_x = 128;            // option: x rows per tile of the tensor-core counting kernel (128: one CTA per SM, 64: two)
     int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
     // scratch

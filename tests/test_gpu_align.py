@@ -624,7 +624,7 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
             part = engine.count_rect(37, nx - 50, 11, ny - 29)
         finally:
             engine.set_option("count_kernel", 0)
-            engine.set_option("tc_tile_x", 64)
+            engine.set_option("tc_tile_x", 128)
         results[kernel, tile_x] = full
         assert np.array_equal(part["counts"], full["counts"][37:nx - 13, 11:ny - 18])
         assert np.array_equal(part["metrics"], full["metrics"][37:nx - 13, 11:ny - 18], equal_nan=True)
