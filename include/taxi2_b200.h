@@ -138,7 +138,8 @@ int taxi_align_strings_metrics(taxi_ctx* ctx, const int32_t* px, const int32_t* 
  * run as an int8 contraction on the tensor cores (tcgen05 + TMA + TMEM, count_tc.cuh) with the
  * trim rule and the fp64 metrics fused into its epilogue; pair lists, small rectangles and rows
  * too long for its operand layout run on the bit-sliced XOR/popcount kernel (count_planes.cuh).
- * Same results either way (option "count_kernel").
+ * Same results either way (option "count_kernel").  Device pointers: d_counts 16-byte, d_metrics
+ * 32-byte aligned (a pair's four metrics leave as one 256-bit store).
  */
 int taxi_count_rect(taxi_ctx* ctx, int32_t x0, int32_t nx, int32_t y0, int32_t ny, uint32_t flags,
                     int32_t* out_counts, double* out_metrics);

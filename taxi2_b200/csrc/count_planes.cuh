@@ -103,6 +103,7 @@ struct CountArgs {
     long long npairs;
     int32_t* counts;   // [npairs][4] or nullptr
     double* metrics;   // [npairs][4] or nullptr
+    const long long* lntab;   // ln k in fixed point (common.cuh: metrics_from_counts_table) or nullptr: floating-point form
 };
 
 // carry-save adder over three bit vectors: s = bit sum, c = carries (weight 2)
@@ -168,16 +169,19 @@ __device__ __forceinline__ int gaps_outside_trim(FX xat, FY yat, int2 sx, int2 s
     return out;
 }
 
-__device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int n, int tv, int ts, int gap)
+// shared_tab: the table staged in shared memory by the caller (tensor-core kernel), else it is read through L1
+__device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int n, int tv, int ts, int gap, const long long* shared_tab = nullptr)
 {
     const int same = n - tv - ts;
     if (a.counts) *reinterpret_cast<int4*>(a.counts + 4 * p) = make_int4(same, ts, tv, gap);
     if (a.metrics) {
         double m[4];
-        metrics_from_counts(same, ts, tv, gap, m);
-        double2* dst = reinterpret_cast<double2*>(a.metrics + 4 * p);
-        dst[0] = make_double2(m[0], m[1]);
-        dst[1] = make_double2(m[2], m[3]);
+        if (shared_tab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return shared_tab[k]; });
+        else if (a.lntab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return __ldg(a.lntab + k); });
+        else metrics_from_counts(same, ts, tv, gap, m);
+        // one 256-bit store per pair (STG.256, sm_100): every lane writes a whole 32-byte sector; two 128-bit
+        // stores would each touch half of every sector of the warp's 1 KB and double the L2 write transactions
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(a.metrics + 4 * p), "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]) : "memory");
     }
 }
 

@@ -236,6 +236,16 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // ---- epilogue: every warp ------------------------------------------------------------------
     mbar_wait(accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // every MMA has completed, so the operand stages are free: the logarithm table of the metric epilogue
+    // (common.cuh: metrics_from_counts_table) takes their place, entries 0 .. 3 * (common columns)
+    const long long* shared_tab = nullptr;
+    if (a.lntab != nullptr && a.metrics != nullptr) {
+        long long* tab = reinterpret_cast<long long*>(smem);
+        const int entries = min(3 * min(a.x.W, a.y.W) * 32 + 1, LN_TABLE_SIZE);
+        for (int k = threadIdx.x; k < entries; k += G::THREADS) tab[k] = __ldg(a.lntab + k);
+        __syncthreads();
+        shared_tab = tab;
+    }
     {
         const int q = warp & 3;                          // this warp reaches TMEM lanes [32 q, 32 q + 32): its 32 y columns
         const int cg = warp >> 2;                        // its 16 x rows of the tile
@@ -264,7 +274,7 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     if (n > 0 && gap > 0)
                         gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xs); }, [&](int w) { return a.y.at(w, ys); },
                                                  __ldg(a.x.span + xs), sy);
-                    store_pair(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0);
+                    store_pair(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0, shared_tab);
                 }
             }
         }

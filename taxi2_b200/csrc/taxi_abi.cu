@@ -118,6 +118,8 @@ struct taxi_ctx {
     int force_top = 0;              // option: packed kernel without the bottom-aligned variant
     int sort_columns = 1;           // option: visit the columns of a rectangle longest first when their lengths differ
     int no_coop = 0;                // option: never use the intra-task kernel for long pairs
+    int metric_tables = 1;          // option: alignment-free kernels take JC / K2P from the fixed-point logarithm table where rows are short enough
+    DevBuf<long long> lntab;        // ln k * 2^58, k = 0 .. 3 * LN_TABLE_COLS
     int tc_tile_x = 128;            // option: x rows per tile of the tensor-core counting kernel (128: one CTA per SM, 64: two)
     int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
@@ -638,6 +640,13 @@ int taxi_ctx_create(int device, taxi_ctx** out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = c->status.reserve(1);
     if (e == cudaSuccess) e = cudaMemset(c->status.p, 0, sizeof(int));
+    if (e == cudaSuccess) {
+        // ln k in fixed point for the table form of the metric epilogue (common.cuh); long double carries 64 bits
+        std::vector<long long> tab(LN_TABLE_SIZE, 0);
+        for (int k = 1; k < LN_TABLE_SIZE; ++k) tab[k] = (long long)llroundl(logl((long double)k) * 0x1p58L);
+        e = c->lntab.reserve(LN_TABLE_SIZE);
+        if (e == cudaSuccess) e = cudaMemcpy(c->lntab.p, tab.data(), LN_TABLE_SIZE * sizeof(long long), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { taxi_ctx_destroy(c); return fail(TAXI_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = c;
     return TAXI_OK;
@@ -649,7 +658,7 @@ void taxi_ctx_destroy(taxi_ctx* c)
     DeviceGuard device_guard_(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& s : c->set) { s.bytes.release(); s.codes.release(); s.d_off.release(); s.planes.release(); s.span.release(); s.tcops.release(); }
-    c->d_codebook.release();
+    c->d_codebook.release(); c->lntab.release();
     c->trace.release(); c->bnd.release(); c->counter.release(); c->status.release();
     c->d_px.release(); c->d_py.release(); c->d_xrows.release(); c->d_ycols.release(); c->d_units.release(); c->d_score.release(); c->d_counts.release(); c->d_metrics.release();
     c->d_alnx.release(); c->d_alny.release(); c->d_alnoff.release(); c->d_alnstart.release();
@@ -1208,6 +1217,9 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
     const SeqSet& Y = yset(c);
     a.x = Planes{X.planes.p, X.span.p, X.W, X.n};
     a.y = Planes{Y.planes.p, Y.span.p, Y.W, Y.n};
+    // one decision per job (it depends on the loaded sets only), so every kernel and every tile of a sharded
+    // job computes JC / K2P the same way
+    a.lntab = (c->metric_tables && std::min(X.W, Y.W) * 32 <= LN_TABLE_COLS) ? c->lntab.p : nullptr;
     if (a.px) {
         CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
         const long long blocks = (a.npairs + 255) / 256;
@@ -1286,6 +1298,8 @@ int taxi_count_rect_device(taxi_ctx* c, int32_t x0, int32_t nx, int32_t y0, int3
     a.px = a.py = nullptr; a.x0 = x0; a.y0 = y0; a.nx = nx; a.ny = ny; a.npairs = npairs;
     a.counts = (flags & TAXI_OUT_COUNTS) ? d_counts : nullptr;
     a.metrics = (flags & TAXI_OUT_METRICS) ? d_metrics : nullptr;
+    // the kernels write a pair's counts with one 128-bit and its metrics with one 256-bit store
+    if (((uintptr_t)a.counts & 15) || ((uintptr_t)a.metrics & 31)) return fail(TAXI_E_ARG, "d_counts must be 16-byte and d_metrics 32-byte aligned");
     return enqueue_count(c, a);
 }
 
@@ -1410,6 +1424,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (std::strcmp(key, "force_top") == 0) { c->force_top = value; return TAXI_OK; }
     if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
     if (std::strcmp(key, "count_kernel") == 0) { c->count_kernel = value; return TAXI_OK; }
+    if (std::strcmp(key, "metric_tables") == 0) { c->metric_tables = value; return TAXI_OK; }
     if (std::strcmp(key, "tc_tile_x") == 0) {
         if (value != 64 && value != 128) return fail(TAXI_E_ARG, "tc_tile_x must be 64 or 128");
         c->tc_tile_x = value;

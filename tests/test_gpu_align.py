@@ -640,6 +640,53 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
     assert_metrics_close(results[2]["metrics"][px, py], want["metrics"])
 
 
+def test_table_form_of_the_metric_epilogue(engine):
+    """Rows of at most 2048 columns take JC / K2P from a fixed-point table of ln k (exact integer
+    differences) instead of the floating-point formula.  Every (n, ts, tv) combination short rows
+    can produce -- including the ones whose logarithm argument is exactly zero, where the
+    reference's rounding decides between None and a finite value -- against the oracle and against
+    the floating-point form of the same kernels: same NaN pattern, p / p-gaps bit for bit, JC / K2P
+    within 1e-12 (measured: 1.4e-13 at worst, tools/metrics_table_check.c)."""
+    from taxi2_b200.engine import pack_strings
+
+    rng = np.random.default_rng(31)
+    rows = []
+    for length in (1, 2, 3, 4, 5, 6, 8, 9, 12, 16, 33, 64):
+        base = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), length)
+        for _ in range(28):
+            s = base.copy()
+            hit = rng.random(length) < rng.choice([0.0, 0.2, 0.5, 0.9])
+            s[hit] = rng.choice(np.frombuffer(b"ACGT-N", dtype=np.uint8), int(hit.sum()))
+            rows.append(s.tobytes().decode().ljust(64, "-"))
+    engine.load(rows, 0)
+    n = len(rows)
+    got = {}
+    for tables in (1, 0):
+        engine.set_option("metric_tables", tables)
+        try:
+            for kernel in (1, 2):
+                engine.set_option("count_kernel", kernel)
+                got[tables, kernel] = engine.count_rect(0, n, 0, n)
+        finally:
+            engine.set_option("count_kernel", 0)
+            engine.set_option("metric_tables", 1)
+    data, off = pack_strings(rows)
+    px, py = np.divmod(np.arange(n * n, dtype=np.int32), n)
+    want = oracle.count_pairs(data, off, px.astype(np.int32), py.astype(np.int32))
+    for key, res in got.items():
+        assert np.array_equal(res["counts"].reshape(-1, 4), want["counts"]), key
+        assert_metrics_close(res["metrics"].reshape(-1, 4), want["metrics"])
+    assert np.array_equal(got[1, 1]["metrics"], got[1, 2]["metrics"], equal_nan=True)      # both kernels, same arithmetic
+    assert np.array_equal(got[0, 1]["metrics"], got[0, 2]["metrics"], equal_nan=True)
+    both = ~np.isnan(got[1, 1]["metrics"][..., 2:])
+    assert np.array_equal(both, ~np.isnan(got[0, 1]["metrics"][..., 2:])) and both.sum() > 1000
+    a, b = got[1, 1]["metrics"][..., 2:][both], got[0, 1]["metrics"][..., 2:][both]
+    assert np.all(np.abs(a - b) <= 5e-13 * np.abs(b))
+    counts = want["counts"]
+    nn, ts, tv = counts[:, :3].sum(axis=1), counts[:, 1], counts[:, 2]
+    assert ((nn > 0) & (nn - 2 * ts - tv == 0)).any() and ((nn > 0) & (nn - 2 * tv == 0)).any() and ((nn > 0) & (3 * nn - 4 * (ts + tv) == 0)).any()
+
+
 def test_intra_task_kernel_for_few_long_pairs(engine):
     """A handful of pairs spanning many stripes: the stripes of each pair are pipelined over the
     warps of a CTA (gotoh_coop_kernel) instead of one warp running them all.  Same scores, counts
