@@ -113,6 +113,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "DONE:\n"
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same with a pause between polls: for the thousand epilogue threads that wait out the whole contraction --
+// polling flat out they take issue slots from the two threads that drive it (and from a co-resident CTA)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -234,7 +250,7 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     __syncwarp();
 
     // ---- epilogue: every warp ------------------------------------------------------------------
-    mbar_wait(accum_full, 0);
+    mbar_wait_relaxed(accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // every MMA has completed, so the operand stages are free: the logarithm table of the metric epilogue
     // (common.cuh: metrics_from_counts_table) takes their place, entries 0 .. 3 * (common columns)
