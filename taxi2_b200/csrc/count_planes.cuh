@@ -173,17 +173,15 @@ __device__ __forceinline__ int gaps_outside_trim(FX xat, FY yat, int2 sx, int2 s
 __device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int n, int tv, int ts, int gap, const long long* shared_tab = nullptr)
 {
     const int same = n - tv - ts;
-    // results stream out once (48 B per pair, gigabytes per launch): evict-first in L2, so that they do not push
-    // the operand rows / planes every tile re-reads out of it
-    if (a.counts)
-        asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(a.counts + 4 * p), "r"(same), "r"(ts), "r"(tv), "r"(gap) : "memory");
+    if (a.counts) __stcs(reinterpret_cast<int4*>(a.counts + 4 * p), make_int4(same, ts, tv, gap));   // streamed out once
     if (a.metrics) {
         double m[4];
         if (shared_tab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return shared_tab[k]; });
         else if (a.lntab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return __ldg(a.lntab + k); });
         else metrics_from_counts(same, ts, tv, gap, m);
-        // one 256-bit store per pair (STG.256, sm_100): every lane writes a whole 32-byte sector; two 128-bit
-        // stores would each touch half of every sector of the warp's 1 KB and double the L2 write transactions
+        // one 256-bit store per pair (STG.256, sm_100): every lane writes a whole 32-byte sector.  Results stream
+        // out once, gigabytes per launch: evict-first in L2, so that they do not push out the operand rows / planes
+        // every tile re-reads (the policy exists for 256-bit stores only)
         asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(a.metrics + 4 * p), "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]) : "memory");
     }
 }
