@@ -46,6 +46,13 @@ __device__ __forceinline__ uint32_t lop3_xor_or(uint32_t a, uint32_t b, uint32_t
     return r;
 }
 
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // bits of a where c is set, bits of b elsewhere: (0xF0 & 0xAA) | (0xCC & 0x55) = 0xE4
 __device__ __forceinline__ uint32_t lop3_mux(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -74,9 +81,12 @@ __device__ __forceinline__ uint32_t diag_candidate(uint32_t Hd, uint32_t a2, uin
     return ne * negD + Hd;
 }
 
-template <int H> struct Pair16Geom {
+template <int H, bool SYM = false> struct Pair16Geom {
     static constexpr int WORDS = (H + 1) / 2;                 // trace words per (lane, step): 2 rows x 2 pairs each
-    static constexpr int HB = (WORDS * 4 + 15) / 16 * 16;     // bytes per (lane, step)
+    // SYM: one more word, the "no orientation-sensitive tie" bits of the lane's row groups (one bit per two rows
+    // and pair; for H = 21 it takes the padding the 16-byte alignment leaves anyway)
+    static constexpr int HB = ((WORDS + (SYM ? 1 : 0)) * 4 + 15) / 16 * 16;     // bytes per (lane, step)
+    static constexpr int GROUPS = (H + 1) / 2;                // SYM: row groups per lane (bit GROUPS-1-q of a half = group q)
 };
 
 // Warp-parallel first-path traceback over the 4-bit codes.  An iteration looks at the next 32
@@ -110,10 +120,10 @@ struct Walk {
 };
 
 // address of the traceback code of cell (ii, jj); MULTI = arena with several stripes
-template <int H, bool MULTI>
+template <int H, bool MULTI, bool SYM = false>
 __device__ __forceinline__ const uint8_t* trace_addr(const Walk& w, const uint8_t* trace, int l0, int ii, int jj)
 {
-    constexpr int HB = Pair16Geom<H>::HB;
+    constexpr int HB = Pair16Geom<H, SYM>::HB;
     const int slot = w.off + ii - 1;   // row -> register slot (top-aligned: off = 0)
     int st = 0, q = slot;
     if (MULTI) { st = slot / (32 * H); q = slot % (32 * H); }
@@ -122,14 +132,26 @@ __device__ __forceinline__ const uint8_t* trace_addr(const Walk& w, const uint8_
     return trace + ((size_t)(st * w.stride + jj - 1 + l - first) * 32 + l) * HB + 2 * r + w.half;
 }
 
-template <int H, bool MULTI>
+template <int H, bool MULTI, bool SYM = false>
 __device__ __forceinline__ void walk_fetch(const AlignArgs& a, Walk& w, int lane, const uint8_t* trace, int l0)
 {
     const int di = (w.state != 2), dj = (w.state != 1);
     const int ii = w.i - lane * di, jj = w.j - lane * dj;
     w.tb = 0; w.ca = 0; w.cb = 0;
+    if (SYM && w.entered && w.state == 1 && w.i > 0 && w.j > 0) {
+        // Orientation.  The path of (y, x) is the transpose of this one unless the winner of H at a cell the
+        // path enters in its H state (the end cell, the cell after every diagonal move) is Ix with Iy at the
+        // same score: Biopython prefers Ix; transposed, the roles swap.  The aligner left one bit per group of
+        // two rows, lane and column: clear if such a tie exists in the group (warp-uniform, rare: one load).
+        constexpr int HB = Pair16Geom<H, true>::HB, WORDS = Pair16Geom<H, true>::WORDS, GROUPS = Pair16Geom<H, true>::GROUPS;
+        const int slot = w.off + w.i - 1, l = slot / H, r = slot % H;
+        const uint8_t* at = trace + ((size_t)(w.j - 1 + l - l0) * 32 + l) * HB + 4 * WORDS;
+        TAXI_CHECK(a, at >= trace && at + 4 <= trace + a.trace_per_warp, 6);
+        const uint32_t bits = __ldcg(reinterpret_cast<const uint32_t*>(at));
+        if (!((bits >> (16 * w.half + GROUPS - 1 - (r >> 1))) & 1u)) w.sens = true;
+    }
     if (w.i > 0 && w.j > 0 && ii >= 1 && jj >= 1) {
-        const uint8_t* at = trace_addr<H, MULTI>(w, trace, l0, ii, jj);
+        const uint8_t* at = trace_addr<H, MULTI, SYM>(w, trace, l0, ii, jj);
         TAXI_CHECK(a, at >= trace && at < trace + a.trace_per_warp, 1);
         w.tb = (int)__ldcg(at);
         w.ca = (int)__ldg(w.x + ii - 1);
@@ -153,15 +175,7 @@ __device__ __forceinline__ void walk_advance(Walk& w, const AlignArgs& a, int la
     const unsigned cont = __ballot_sync(TAXI_FULL_MASK, ns == state);
     const int V = min(__ffs(~cont | 0x80000000u), nvalid);   // cells visited: up to and including the first hand-over
     const int next = __shfl_sync(TAXI_FULL_MASK, ns, V - 1);
-    if (SYM) {
-        // Orientation.  The path of (y, x) is the transpose of this one unless the winner of H at a
-        // cell the path enters is Ix with Iy at the same score (Biopython prefers Ix; transposed, the
-        // roles swap).  Bit 4 of a cell's code is CLEAR where Ix and Iy tie at that cell.  The path enters a cell in its H
-        // state at the start and after every diagonal move; if that state is Ix, the cell is the first
-        // one (lane 0) of the window this iteration looks at.
-        if (w.entered && state == 1 && !(__shfl_sync(TAXI_FULL_MASK, tb, 0) & 16)) w.sens = true;
-        w.entered = (state == 0);
-    }
+    if (SYM) w.entered = (state == 0);   // the next cell is entered in its H state after a diagonal move (walk_fetch looks)
     const bool mine = lane < V;
     const unsigned visited = 0xffffffffu >> (32 - V);
     const Fast16& f = a.f16;
@@ -276,8 +290,8 @@ __device__ __forceinline__ void traceback_two(const AlignArgs& a, int lane, cons
 {
     if (!second) { wb.i = 0; wb.j = 0; }
     while ((wa.i > 0 && wa.j > 0) || (wb.i > 0 && wb.j > 0)) {
-        walk_fetch<H, MULTI>(a, wa, lane, trace, l0);
-        walk_fetch<H, MULTI>(a, wb, lane, trace, l0);
+        walk_fetch<H, MULTI, SYM>(a, wa, lane, trace, l0);
+        walk_fetch<H, MULTI, SYM>(a, wb, lane, trace, l0);
         walk_advance<SYM>(wa, a, lane);
         walk_advance<SYM>(wb, a, lane);
     }
@@ -427,13 +441,13 @@ __device__ __forceinline__ void align_two(const AlignArgs& a, long long p0, long
 // reproduces the leading end gap by itself (requires internal extend == end extend, checked on
 // the host).  No per-row constant registers are needed; dead slots above row 0 idle at "minus
 // infinity".
-// SYM: every cell's code also says (bit 4 clear) whether Ix and Iy hold the same score there -- the one
-// decision that differs when the pair is aligned the other way round; see walk_advance.
+// SYM: besides the codes, one bit per group of two rows says whether H is won there by Ix with Iy at the same
+// score -- the one decision that differs when the pair is aligned the other way round; see walk_fetch.
 template <int H, bool SYM = false>
 __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p0, long long p1, int lane, uint8_t* trace)
 {
-    constexpr int HB = Pair16Geom<H>::HB;
-    constexpr int WORDS = Pair16Geom<H>::WORDS;
+    constexpr int HB = Pair16Geom<H, SYM>::HB;
+    constexpr int WORDS = Pair16Geom<H, SYM>::WORDS;
     constexpr int SL = 32 * H;
     const Fast16& f = a.f16;
     const PairRef A = pair_ref(a, p0), B = pair_ref(a, p1);
@@ -511,22 +525,25 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 uint32_t tw[WORDS];
                 uint32_t tprev = 0;
                 uint32_t Mr = diag_candidate(Hd_saved, a2[0], b2, f.negD);
+                uint32_t ties = 0, zprev = 0;   // SYM
 #pragma unroll
                 for (int r = 0; r < H; ++r) {
                     uint32_t Mr_next = 0;
                     if (r + 1 < H) Mr_next = diag_candidate(Hl[r], a2[r + 1], b2, f.negD);   // needs H(i, j-1) before it is overwritten
                     const uint32_t Yin = Yn[r];
-                    uint32_t tc = lop3_or3(Mr, Xin, Yin);
+                    const uint32_t tc = lop3_or3(Mr, Xin, Yin);
                     const uint32_t Mt = lop3_and_or(Mr, F16_CLEAN, 0x00030003u);
                     const uint32_t Xt = lop3_and_or(Xin, F16_CLEAN, 0x00020002u);
                     const uint32_t Yt = lop3_and_or(Yin, F16_CLEAN, 0x00010001u);
                     Hl[r] = __vimax3_u16x2(Mt, Xt, Yt);
                     if constexpr (SYM) {
-                        // Xt ^ Yt is 3 per half exactly where Ix and Iy hold the same score (tags 2 and 1), at
-                        // least 16 elsewhere: min(., 16) sets bit 4 where they do NOT tie, and one LOP3 takes
-                        // the low nibble from the code and the rest from that (LOP3 + VIMNMX + LOP3 per row pair)
-                        const uint32_t nt = __vminu2(Xt ^ Yt, 0x00100010u);
-                        tc = lop3_mux(tc, nt, 0x000F000Fu);
+                        // H ^ Iy ^ 3 is zero per half exactly where H holds Ix's value (tag 2) and Iy the same score
+                        // (tag 1).  min3 over the two rows of a group and 1 gives "no such tie in the group", shifted
+                        // into the lane's bit string on the fma pipe: 2 LOP3 + VIMNMX3 + IMAD per two row pairs.
+                        const uint32_t z = lop3_xor3(Hl[r], Yt, 0x00030003u);
+                        if (r & 1) ties = ties * 2u + __vimin3_u16x2(zprev, z, 0x00010001u);
+                        else if (r == H - 1) ties = ties * 2u + __vminu2(z, 0x00010001u);
+                        zprev = z;
                     }
                     Xin = __viaddmax_u16x2(Mt, ncXM, Xt + cXX);
                     Yn[r] = __viaddmax_u16x2(Mt, (r == H - 1) ? ncYMl : ncYMi, Yt + ((r == H - 1) ? cYYl : cYYi));
@@ -544,7 +561,7 @@ __device__ __forceinline__ void align_two_bottom(const AlignArgs& a, long long p
                 for (int k = 0; k < HB / 16; ++k) {
                     uint32_t w[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) w[q] = (4 * k + q < WORDS) ? tw[4 * k + q] : 0u;
+                    for (int q = 0; q < 4; ++q) w[q] = (4 * k + q < WORDS) ? tw[4 * k + q] : ((SYM && 4 * k + q == WORDS) ? ties : 0u);
                     __stcg(dst + k, make_uint4(w[0], w[1], w[2], w[3]));
                 }
             }

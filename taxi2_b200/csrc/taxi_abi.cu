@@ -249,7 +249,7 @@ const Dispatch kDispatch16b[] = {P16(8, 1), P16(12, 1), P16(16, 1), P16(21, 1), 
 const Dispatch kDispatch16m[] = {P16(16, 2), P16(21, 2), P16(24, 2), P16(32, 2)};
 #undef P16
 // bottom-aligned, "both orientations" (the code of every cell also records Ix / Iy ties, the walk mirrors the result)
-#define P16S(H) {H, occupancy16s<H>, launch_pair16s<H>, Pair16Geom<H>::HB}
+#define P16S(H) {H, occupancy16s<H>, launch_pair16s<H>, Pair16Geom<H, true>::HB}
 const Dispatch kDispatch16s[] = {P16S(8), P16S(12), P16S(16), P16S(21), P16S(24), P16S(32)};
 #undef P16S
 
