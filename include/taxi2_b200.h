@@ -216,6 +216,23 @@ int taxi_aggregate_subsets(const double* metrics, const uint8_t* undefined, int3
                            double* sum, double* vmin, double* vmax, int64_t* count, int64_t* first_seen, int64_t* next_order);
 
 /*
+ * The subset statistics files of versusAll (subsets/<partition>/linear/{pairs,identity}.tsv and
+ * matricial/<metric>.tsv; versus_all.py:143-249, 647-684) from the arrays of taxi_aggregate_subsets, gathered
+ * in first-seen key order: kx / ky = subset ids of a key (indices into the label table), mean / min / max /
+ * count per metric in that order.  _rows appends one row per selected key (headers stay in Python),
+ * _matrix writes a whole matrix file (runs of equal kx are its rows; t0..t3 are the pieces of the statistics
+ * template around {mean}, {min}, {max}).  "NA" where count is 0.
+ */
+int taxi_format_subset_rows(const char* path, const char* label_bytes, const int64_t* label_off,
+                            const int32_t* kx, const int32_t* ky, const uint8_t* select, int64_t nkeys, int32_t with_query,
+                            int32_t nmetrics, const double* const* mean, const double* const* vmin, const double* const* vmax,
+                            const int64_t* const* count, const char* float_format, int32_t threads);
+int taxi_format_subset_matrix(const char* path, const char* label_bytes, const int64_t* label_off,
+                              const int32_t* kx, const int32_t* ky, int64_t nkeys,
+                              const double* mean, const double* vmin, const double* vmax, const int64_t* count,
+                              const char* float_format, const char* t0, const char* t1, const char* t2, const char* t3, int32_t threads);
+
+/*
  * Page-locked host buffers for the host-facing calls above: results land in them with an
  * asynchronous DMA instead of a staged pageable copy.  Plain malloc'ed buffers work too.
  */

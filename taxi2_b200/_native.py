@@ -68,6 +68,10 @@ SIGNATURES = {
     "taxi_format_values": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "taxi_aggregate_subsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "taxi_format_subset_rows": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int32]),
+    "taxi_format_subset_matrix": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]),
     "taxi_host_alloc": (C.c_void_p, [C.c_int64]),
     "taxi_host_free": (None, [C.c_void_p]),
     "taxi_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int]),

@@ -14,6 +14,7 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <sys/types.h>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -316,6 +317,80 @@ int taxi_aggregate_subsets(const double* metrics, const uint8_t* undefined, int3
         }
     }
     return TAXI_OK;
+}
+
+// subsets/<partition>/linear/{pairs,identity}.tsv (versus_all.py:143-205, 647-684): one row per selected key
+// (subset_x, subset_y) in first-seen order -- the label of subset_x, the label of subset_y when with_query,
+// then mean / min / max of every metric, "NA" where no distance was defined.  Rows are appended; the
+// header stays in Python.  A partition of S subsets has up to S^2 keys: a million rows for a thousand
+// species, formerly a dozen Python strings each.
+int taxi_format_subset_rows(const char* path, const char* label_bytes, const int64_t* label_off,
+                            const int32_t* kx, const int32_t* ky, const uint8_t* select, int64_t nkeys, int32_t with_query,
+                            int32_t nmetrics, const double* const* mean, const double* const* vmin, const double* const* vmax,
+                            const int64_t* const* count, const char* float_format, int32_t threads)
+{
+    if (!path || !label_bytes || !label_off || !kx || !ky || nkeys < 0 || nkeys > INT32_MAX || nmetrics < 0 || !float_format) return TAXI_E_ARG;
+    if (nmetrics > 0 && (!mean || !vmin || !vmax || !count)) return TAXI_E_ARG;
+    const Table labels{label_bytes, label_off};
+    const ValueFormat vf(float_format);
+    auto fn = [&](int32_t b, int32_t e, std::string& out) {
+        out.reserve((size_t)(e - b) * (size_t)(24 + 24 * nmetrics));
+        for (int32_t k = b; k < e; ++k) {
+            if (select && !select[k]) continue;
+            labels.append(out, kx[k]);
+            if (with_query) { out += '\t'; labels.append(out, ky[k]); }
+            for (int32_t m = 0; m < nmetrics; ++m) {
+                const bool none = count[m][k] == 0;
+                out += '\t'; append_value(out, none ? 0.0 : mean[m][k], none, 1.0, vf, "NA");
+                out += '\t'; append_value(out, none ? 0.0 : vmin[m][k], none, 1.0, vf, "NA");
+                out += '\t'; append_value(out, none ? 0.0 : vmax[m][k], none, 1.0, vf, "NA");
+            }
+            out += '\n';
+        }
+    };
+    return format_rows(path, (int32_t)nkeys, threads, fn);
+}
+
+// subsets/<partition>/matricial/<metric>.tsv (versus_all.py:207-249): the keys in first-seen order cut into runs of
+// equal subset_x (the reference flushes a matrix row whenever subset_x changes); the first run is preceded by the
+// header (an empty cell, then its subset_y labels); a cell is t0 mean t1 min t2 max t3 -- the pieces of the
+// statistics template around its three fields -- or "NA" where no distance was defined.  The whole file.
+int taxi_format_subset_matrix(const char* path, const char* label_bytes, const int64_t* label_off,
+                              const int32_t* kx, const int32_t* ky, int64_t nkeys,
+                              const double* mean, const double* vmin, const double* vmax, const int64_t* count,
+                              const char* float_format, const char* t0, const char* t1, const char* t2, const char* t3, int32_t threads)
+{
+    if (!path || !label_bytes || !label_off || !kx || !ky || nkeys < 0 || nkeys > INT32_MAX || !float_format || !t0 || !t1 || !t2 || !t3) return TAXI_E_ARG;
+    if (nkeys > 0 && (!mean || !vmin || !vmax || !count)) return TAXI_E_ARG;
+    const Table labels{label_bytes, label_off};
+    const ValueFormat vf(float_format);
+    std::vector<int64_t> starts;
+    for (int64_t k = 0; k < nkeys; ++k) if (k == 0 || kx[k] != kx[k - 1]) starts.push_back(k);
+    starts.push_back(nkeys);
+    const int32_t nruns = (int32_t)starts.size() - 1;
+    { const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644); if (fd < 0) return TAXI_E_ARG; ::close(fd); }
+    if (nruns == 0) return TAXI_OK;
+    auto fn = [&](int32_t b, int32_t e, std::string& out) {
+        out.reserve((size_t)(starts[e] - starts[b]) * 40 + 64);
+        for (int32_t r = b; r < e; ++r) {
+            const int64_t lo = starts[r], hi = starts[r + 1];
+            if (r == 0) {
+                for (int64_t k = lo; k < hi; ++k) { out += '\t'; labels.append(out, ky[k]); }
+                out += '\n';
+            }
+            labels.append(out, kx[lo]);
+            for (int64_t k = lo; k < hi; ++k) {
+                out += '\t';
+                if (count[k] == 0) { out += "NA"; continue; }
+                out += t0; append_value(out, mean[k], false, 1.0, vf, "NA");
+                out += t1; append_value(out, vmin[k], false, 1.0, vf, "NA");
+                out += t2; append_value(out, vmax[k], false, 1.0, vf, "NA");
+                out += t3;
+            }
+            out += '\n';
+        }
+    };
+    return format_rows(path, nruns, threads, fn);
 }
 
 }  // extern "C"

@@ -110,6 +110,32 @@ def format_values(values: np.ndarray, undefined: np.ndarray | None, fmt: str, mi
         cap = -got + 64
 
 
+def _pointer_array(arrays):
+    return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+
+def format_subset_rows(path, labels: StringTable, kx, ky, select, with_query: bool, mean, vmin, vmax, count, fmt: str, threads=0) -> None:
+    """Append the rows of subsets/*/linear/{pairs,identity}.tsv for the selected keys (first-seen order):
+    labels, then mean / min / max per metric (lists of per-metric arrays over the keys), "NA" where count is 0."""
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for group in (mean, vmin, vmax) for a in group]
+    m = len(mean)
+    cnt = [np.ascontiguousarray(a, dtype=np.int64) for a in count]
+    select = np.ascontiguousarray(select, dtype=np.uint8)
+    N.check(N.load().taxi_format_subset_rows(str(path).encode(), labels.bytes_ptr, labels.off_ptr, _ptr(kx), _ptr(ky), _ptr(select), len(kx),
+                                             int(bool(with_query)), m, _pointer_array(keep[:m]), _pointer_array(keep[m:2 * m]),
+                                             _pointer_array(keep[2 * m:]), _pointer_array(cnt), fmt.encode(), threads))
+
+
+def format_subset_matrix(path, labels: StringTable, kx, ky, mean, vmin, vmax, count, fmt: str, pieces, threads=0) -> None:
+    """Write one subsets/*/matricial/<metric>.tsv: runs of equal kx are its rows, `pieces` the four strings
+    around {mean}, {min}, {max} in the statistics template."""
+    arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, vmin, vmax)]
+    cnt = np.ascontiguousarray(count, dtype=np.int64)
+    N.check(N.load().taxi_format_subset_matrix(str(path).encode(), labels.bytes_ptr, labels.off_ptr, _ptr(kx), _ptr(ky), len(kx),
+                                               _ptr(arrays[0]), _ptr(arrays[1]), _ptr(arrays[2]), _ptr(cnt), fmt.encode(),
+                                               *[piece.encode("utf-8") for piece in pieces], threads))
+
+
 class NativeSubsetState:
     """sum / min / max / n / first-seen per (subset_x, subset_y) of one metric column."""
 

@@ -464,6 +464,31 @@ class SubsetAggregation:
         ty = [label_of[k] for k in ky.tolist()]
         form = fmt.float.format
         fmtc = fastwrite.printf_format(fmt.float)
+        import re
+        plain = re.match(r"^([^{}]*)\{mean\}([^{}]*)\{min\}([^{}]*)\{max\}([^{}]*)$", fmt.stats_template)
+        heads = [f"{label} {stat}" for label in labels for stat in ("mean", "min", "max")]
+        if fmtc and plain:
+            # plain float spec and a plain statistics template: the library writes every row (a partition of a
+            # thousand species has a million keys; a dozen Python strings per key took most of a large run's tail)
+            table = fastwrite.StringTable(label_of)
+            kx32, ky32 = kx.astype(np.int32), ky.astype(np.int32)
+            cnts = [st.count[keys] for st in states]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                means = [st.sum[keys] / c for st, c in zip(states, cnts)]
+            mins, maxs = [st.min[keys] for st in states], [st.max[keys] for st in states]
+            linear = path / "linear"
+            linear.mkdir(parents=True, exist_ok=True)
+            for name, select, lead in (("pairs.tsv", kx != ky, ("target", "query")), ("identity.tsv", kx == ky, ("target",))):
+                with open(linear / name, "w", newline="") as f:
+                    if select.any():
+                        f.write("\t".join((*lead, *heads)) + "\n")
+                if select.any():
+                    fastwrite.format_subset_rows(linear / name, table, kx32, ky32, select, len(lead) == 2, means, mins, maxs, cnts, fmtc)
+            matricial = path / "matricial"
+            matricial.mkdir(parents=True, exist_ok=True)
+            for label, mean, mn, mx, cnt in zip(labels, means, mins, maxs, cnts):
+                fastwrite.format_subset_matrix(matricial / f"{label}.tsv", table, kx32, ky32, mean, mn, mx, cnt, fmtc, plain.groups())
+            return
 
         def column(values, counts):
             if fmtc:   # plain float spec: the library formats the whole column in one call
@@ -476,7 +501,6 @@ class SubsetAggregation:
             with np.errstate(invalid="ignore", divide="ignore"):
                 mean = st.sum[keys] / cnt
             stats.append((column(mean, cnt), column(st.min[keys], cnt), column(st.max[keys], cnt), cnt))
-        heads = [f"{label} {stat}" for label in labels for stat in ("mean", "min", "max")]
         linear = path / "linear"
         linear.mkdir(parents=True, exist_ok=True)
         same = (kx == ky).tolist()
@@ -498,8 +522,6 @@ class SubsetAggregation:
         # runs of equal first subset (the reference flushes a matrix row whenever idx changes)
         starts = [0] + [k for k in range(1, len(keys)) if kx[k] != kx[k - 1]] + [len(keys)] if len(keys) else [0]
         template = fmt.stats_template
-        import re
-        plain = re.match(r"^([^{}]*)\{mean\}([^{}]*)\{min\}([^{}]*)\{max\}([^{}]*)$", template)
         for label, (mean, mn, mx, cnt) in zip(labels, stats):
             has = cnt.tolist()
             if plain:   # "{mean} ({min}-{max})" and the like: concatenation instead of 1e6 str.format calls

@@ -199,3 +199,42 @@ def test_fixed_point_fast_path_equals_python_format(tmp_path, spec):
     got = path.read_text().rstrip("\n").split("\t")[1:]
     want = [spec.format(v) for v in vals]
     assert got == want
+
+
+@pytest.mark.parametrize("template", ["{mean} ({min}-{max})", "[{mean}|{min}|{max}]", "{mean}"])
+def test_subset_statistics_files_native_rows_equal_the_python_rows(tmp_path, monkeypatch, template):
+    """subsets/*/linear/{pairs,identity}.tsv and matricial/<metric>.tsv (versus_all.py:143-249): the
+    library's row writers against the Python string assembly of the same arrays -- keys in
+    first-seen order, a subset that is None ("?"), keys without any defined distance ("NA"),
+    several runs of equal first subset, values on decimal rounding ties.  A statistics template
+    that is not the three fields in order keeps the Python rows."""
+    from types import SimpleNamespace
+
+    from taxi2_b200.tasks.versus_all import SubsetAggregation
+
+    rng = np.random.default_rng(12)
+    names = ["Alpha beta", None, "Gamma", "Delta epsilon zeta", "Eta"]
+    nsub = len(names)
+    labels = ["p-distance", "k2p"]
+    states = []
+    order = rng.permutation(nsub * nsub)[: nsub * nsub - 3]          # three keys never seen
+    for _ in labels:
+        st = fw.NativeSubsetState(nsub)
+        st.first_seen[order] = np.arange(len(order))
+        st.count[order] = rng.integers(0, 4, len(order))
+        seen = order[st.count[order] > 0]
+        st.sum[seen] = np.round(rng.random(len(seen)) * 3, 5)
+        st.min[seen] = np.round(rng.random(len(seen)), 5)
+        st.max[seen] = np.round(rng.random(len(seen)) + 1, 4) + 0.00005
+        states.append(st)
+    agg = SubsetAggregation.__new__(SubsetAggregation)
+    agg.native = (names, labels, states)
+    fmt = SimpleNamespace(float="{:.4f}", stats_template=template)
+    agg.write_arrays(tmp_path / "native", fmt)
+    monkeypatch.setattr(fw, "printf_format", lambda spec: None)      # the Python rows of the same method
+    agg.write_arrays(tmp_path / "python", fmt)
+    files = sorted(p.relative_to(tmp_path / "python") for p in (tmp_path / "python").rglob("*.tsv"))
+    assert [str(f) for f in files] == ["linear/identity.tsv", "linear/pairs.tsv", "matricial/k2p.tsv", "matricial/p-distance.tsv"]
+    for rel in files:
+        assert (tmp_path / "native" / rel).read_bytes() == (tmp_path / "python" / rel).read_bytes(), rel
+    assert b"NA" in (tmp_path / "native" / "linear" / "pairs.tsv").read_bytes() and b"?" in (tmp_path / "native" / "matricial" / "k2p.tsv").read_bytes()
