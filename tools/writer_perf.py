@@ -1,6 +1,7 @@
 """Host side of VersusAll on its own (no GPU): the task driven by a stand-in engine that hands out
 pre-computed random metrics instantly, so what is timed is the block iterator, the undefined-pair
-bookkeeping, the native writers and the subset aggregation.  Usage: writer_perf.py [n] [profile]"""
+bookkeeping, the native writers and the subset aggregation.  Usage: writer_perf.py [n] [pairs] [profile]
+("pairs": also align/aligned_pairs.txt from synthetic gapped strings)"""
 import cProfile
 import json
 import pstats
@@ -40,6 +41,19 @@ class Instant:
     def align_rect(self, x0, nx, y0, ny, want=("metrics",), **kw):
         return {"metrics": self.metrics[x0:x0 + nx, y0:y0 + ny]}
 
+    def align_strings_raw(self, px, py, want=("score",)):
+        """Gapped strings of the same shape the library returns: slots of len(x) + len(y) bytes, the alignment
+        (here: 680 random symbols) right-aligned in each."""
+        k = len(px)
+        off = np.arange(k + 1, dtype=np.int64) * 1300
+        start = off[1:] - 680
+        if getattr(self, "_strings", None) is None or len(self._strings[0]) < k * 1300:
+            rng = np.random.default_rng(2)
+            self._strings = tuple(np.frombuffer(b"ACGTACGTACGTACG-", dtype=np.uint8)[rng.integers(0, 16, k * 1300, dtype=np.uint8)] for _ in range(2))
+        ox, oy = (a[: k * 1300] for a in self._strings)
+        px = np.asarray(px); py = np.asarray(py)
+        return ox, oy, start, off, np.zeros(k, dtype=np.int32), {"metrics": self.metrics[px, py]}
+
     def align_strings(self, px, py):
         return [b"A"] * len(px), [b"C"] * len(px), np.zeros(len(px), dtype=np.int32)
 
@@ -59,9 +73,9 @@ task.work_dir = Path(tempfile.mkdtemp())
 task.progress_handler = lambda *a: None
 task.input.sequences = Sequences(records)
 task.input.species, task.input.genera = species, genera
-task.params.pairs.write = False
+task.params.pairs.write = "pairs" in sys.argv[2:]
 t0 = time.perf_counter()
-if len(sys.argv) > 2:
+if "profile" in sys.argv[2:]:
     prof = cProfile.Profile()
     prof.runcall(task.start)
     pstats.Stats(prof).sort_stats("cumulative").print_stats(25)
