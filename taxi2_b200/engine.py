@@ -84,6 +84,7 @@ class Engine:
         N.check(self._lib.taxi_ctx_create(int(device), C.byref(self._ctx)))
         self.device = int(device)
         self.n = [0, 0]
+        self._string_pool: dict = {}
         self._pinned_pool: dict = {}
         self.set_scores(scores)
 
@@ -207,19 +208,30 @@ class Engine:
         N.check(self._lib.taxi_align_pairs(self._ctx, _p(px), _p(py), len(px), flags, _p(score), _p(counts), _p(metrics)))
         return self._result(score, counts, metrics, None)
 
-    def align_strings_raw(self, px, py, want=("score",)) -> tuple:
+    def align_strings_raw(self, px, py, want=("score",), slot: int | None = None) -> tuple:
         """-> (aln_x, aln_y, start, off, scores[, result dict]): pair k's gapped strings are
         aln_x / aln_y[start[k]:off[k + 1]] (right-aligned in slots of len(x) + len(y) bytes).
         With "counts" / "metrics" in `want` the same launch also fills them (sixth element: the
-        dict align_pairs would return), so strings and distances come from ONE alignment."""
+        dict align_pairs would return), so strings and distances come from ONE alignment.
+        slot: the two string arrays are kept and handed out again by the next call with the same
+        slot -- a block of barcode pairs is 2.6 KB of strings per pair, and first-touching
+        hundreds of fresh megabytes per block costs more than the download itself.  Only for
+        callers that are done with a block's strings before they reuse its slot."""
         px = np.ascontiguousarray(px, dtype=np.int32)
         py = np.ascontiguousarray(py, dtype=np.int32)
         n = len(px)
         off = np.zeros(n + 1, dtype=np.int64)
         N.check(self._lib.taxi_alignment_capacity(self._ctx, _p(px), _p(py), n, _p(off)))
         total = int(off[-1])
-        ox = np.zeros(max(total, 1), dtype=np.uint8)
-        oy = np.zeros(max(total, 1), dtype=np.uint8)
+        if slot is None:
+            ox = np.zeros(max(total, 1), dtype=np.uint8)
+            oy = np.zeros(max(total, 1), dtype=np.uint8)
+        else:
+            kept = self._string_pool.setdefault(int(slot), {})
+            if "x" not in kept or len(kept["x"]) < total:
+                kept["x"] = np.empty(max(total, 1) + total // 8, dtype=np.uint8)
+                kept["y"] = np.empty(max(total, 1) + total // 8, dtype=np.uint8)
+            ox, oy = kept["x"][: max(total, 1)], kept["y"][: max(total, 1)]
         start = np.zeros(max(n, 1), dtype=np.int64)
         flags, score, counts, metrics = self._outputs(n, tuple(want) + ("score",))
         N.check(self._lib.taxi_align_strings_metrics(self._ctx, _p(px), _p(py), n, _p(off), _p(ox), _p(oy), _p(start),

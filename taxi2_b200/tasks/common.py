@@ -158,7 +158,10 @@ def iter_pair_blocks(engine, xs: list[Sequence], ys: list[Sequence] | None, alig
         if align and want_strings:
             px, py = np.divmod(np.arange(nx * ny, dtype=np.int64), ny)
             px, py = (px + x0).astype(np.int32), py.astype(np.int32)
-            ox, oy, start, off, _, res = eng.align_strings_raw(px, py, want=("metrics",))
+            # raw_strings consumers are done with a block's strings before they ask for the next block, so the
+            # arrays can be the ones the third block before it used (no first touch of fresh memory per block);
+            # the per-pair consumers get Python strings decoded from them right here
+            ox, oy, start, off, _, res = eng.align_strings_raw(px, py, want=("metrics",), slot=slot)
             metrics = res["metrics"].reshape(nx, ny, 4)
             if raw_strings:
                 aligned_raw = (ox, oy, start, off)

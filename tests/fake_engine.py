@@ -101,7 +101,7 @@ class OracleEngine:
             ax.append(a.encode("latin-1")); ay.append(b.encode("latin-1")); sc.append(int(round(s)))
         return ax, ay, np.array(sc, dtype=np.int32)
 
-    def align_strings_raw(self, px, py, want=("score",)):
+    def align_strings_raw(self, px, py, want=("score",), slot=None):
         xd, xo = self.sets[0]
         yd, yo = self.sets[1] if self.sets[1] is not None else self.sets[0]
         ax, ay, score = self.align_strings(px, py)

@@ -41,7 +41,7 @@ class Instant:
     def align_rect(self, x0, nx, y0, ny, want=("metrics",), **kw):
         return {"metrics": self.metrics[x0:x0 + nx, y0:y0 + ny]}
 
-    def align_strings_raw(self, px, py, want=("score",)):
+    def align_strings_raw(self, px, py, want=("score",), slot=None):
         """Gapped strings of the same shape the library returns: slots of len(x) + len(y) bytes, the alignment
         (here: 680 random symbols) right-aligned in each."""
         k = len(px)
