@@ -45,6 +45,7 @@
 namespace taxi {
 
 constexpr int TC_TILE = 128;              // pairs per tile side; also bytes of K per pipeline stage
+constexpr int TC_BAND = 12;                // x tiles per band of the CTA order (operand reuse in L2)
 constexpr int TC_UMMA_K = 32;             // bytes of K per tcgen05.mma (8-bit operands)
 constexpr int TC_ROW_SEGMENTS = 8;        // row length in units of Lp
 // Tile geometry: TC_TILE y columns (TMEM lanes) x TX x rows (TMEM columns per accumulator).  TX = 128: one
@@ -183,7 +184,14 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
     const CountArgs& a = args.c;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xt = blockIdx.y * TX, yt = blockIdx.x * TC_TILE;   // tile origin inside the rectangle
+    // Tile of this CTA.  The grid is one-dimensional and walks the tile matrix in bands of TC_BAND x tiles,
+    // inside a band column by column (the band's x tiles of one y tile, then the next y tile): a wave of ~148
+    // CTAs then touches about 12 x tiles and 12 y tiles (16 MB of operand rows) instead of 2 and all 71 (48 MB),
+    // and the operands stay in L2 under the stream of results.
+    const int tiles_y = (a.ny + TC_TILE - 1) / TC_TILE, tiles_x = (a.nx + TX - 1) / TX;
+    const int band = (int)blockIdx.x / (TC_BAND * tiles_y), within = (int)blockIdx.x % (TC_BAND * tiles_y);
+    const int band_rows = min(TC_BAND, tiles_x - band * TC_BAND);
+    const int xt = (band * TC_BAND + within % band_rows) * TX, yt = (within / band_rows) * TC_TILE;   // tile origin inside the rectangle
     const int Lp = args.Lp;
     const int blocks_per_L = Lp / TC_TILE;
     const int kblocks = 6 * blocks_per_L;

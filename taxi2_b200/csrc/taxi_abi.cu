@@ -1246,7 +1246,7 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
             CountTcArgs t{a, std::min(XX.Lp, YY.Lp), XX.Lp, YY.Lp};
             const bool wide = c->tc_tile_x == 128;
             const int tx = wide ? 128 : 64;
-            dim3 grid((unsigned)((a.ny + TC_TILE - 1) / TC_TILE), (unsigned)((a.nx + tx - 1) / tx));
+            dim3 grid((unsigned)(((a.ny + TC_TILE - 1) / TC_TILE) * ((a.nx + tx - 1) / tx)));   // one-dimensional: count_tc_kernel orders the tiles itself
             if (wide) CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcGeom<128>::SMEM));
             else CUDA_TRY(cudaFuncSetAttribute(count_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcGeom<64>::SMEM));
             CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
