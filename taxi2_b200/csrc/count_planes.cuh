@@ -169,7 +169,9 @@ __device__ __forceinline__ int gaps_outside_trim(FX xat, FY yat, int2 sx, int2 s
     return out;
 }
 
-// shared_tab: the table staged in shared memory by the caller (tensor-core kernel), else it is read through L1
+// shared_tab: the table staged in shared memory by the caller (tensor-core kernels, STAGED: they never read it
+// through L1, and leaving that path out keeps their unrolled epilogues a third smaller), else it is read through L1
+template <bool STAGED = false>
 __device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int n, int tv, int ts, int gap, const long long* shared_tab = nullptr)
 {
     const int same = n - tv - ts;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void store_pair(const CountArgs& a, long long p, int 
     if (a.metrics) {
         double m[4];
         if (shared_tab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return shared_tab[k]; });
-        else if (a.lntab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return __ldg(a.lntab + k); });
+        else if (!STAGED && a.lntab) metrics_from_counts_table(same, ts, tv, gap, m, [&](int k) { return __ldg(a.lntab + k); });
         else metrics_from_counts(same, ts, tv, gap, m);
         // one 256-bit store per pair (STG.256, sm_100): every lane writes a whole 32-byte sector.  Results stream
         // out once, gigabytes per launch: evict-first in L2, so that they do not push out the operand rows / planes

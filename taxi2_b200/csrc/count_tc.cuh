@@ -298,7 +298,7 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     if (n > 0 && gap > 0)
                         gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xs); }, [&](int w) { return a.y.at(w, ys); },
                                                  __ldg(a.x.span + xs), sy);
-                    store_pair(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0, shared_tab);
+                    store_pair<true>(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0, shared_tab);
                 }
             }
         }
@@ -307,6 +307,182 @@ count_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     __syncthreads();
     if (warp == 2)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(G::TMEM_COLS));
+}
+
+// ---- persistent form: the contraction of the next tile runs under the epilogue of this one -----------------
+// count_tc_kernel's CTAs all start together, so a whole wave is in its contraction phase (no result traffic)
+// and then in its epilogue (DRAM-bound on the 48 B per pair) at the same time: the two phases add up
+// (0.37 + 0.6 ms on C2) on an SM and across the GPU, with one CTA per SM or with two.  Here one CTA per SM
+// walks a static list of 128 x 64 tiles; the TMA and MMA threads run up to two tiles ahead into the second
+// of two accumulator sets in TMEM (2 x 4 x 64 columns) while 16 epilogue warps drain the first.
+constexpr int TCP_TX = 64;                 // x rows per tile
+constexpr int TCP_STAGES = 5;
+constexpr int TCP_EPI_WARPS = 16;          // warps 4 .. 19: TMEM lane quarter = warp % 4, 16 x rows each
+constexpr int TCP_THREADS = (4 + TCP_EPI_WARPS) * 32;
+constexpr int TCP_STAGE_X = TCP_TX * TC_TILE, TCP_STAGE_Y = TC_TILE * TC_TILE;
+constexpr size_t TCP_SMEM = (size_t)TCP_STAGES * (TCP_STAGE_X + TCP_STAGE_Y) + (size_t)LN_TABLE_SIZE * 8 + 1024;
+
+namespace tc {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tc
+
+__global__ void __launch_bounds__(TCP_THREADS, 1)
+count_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y, const CountTcArgs args)
+{
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sY = smem;
+    uint8_t* sX = smem + TCP_STAGES * TCP_STAGE_Y;
+    long long* tab = reinterpret_cast<long long*>(sX + TCP_STAGES * TCP_STAGE_X);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tab + LN_TABLE_SIZE);
+    uint64_t* empty = full + TCP_STAGES;
+    uint64_t* acc_full = empty + TCP_STAGES;      // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const CountArgs& a = args.c;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Lp = args.Lp;
+    const int blocks_per_L = Lp / TC_TILE;
+    const int kblocks = 6 * blocks_per_L;
+    const int tiles_y = (a.ny + TC_TILE - 1) / TC_TILE, tiles_x = (a.nx + TCP_TX - 1) / TCP_TX;
+    const int ntiles = tiles_x * tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&map_y) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TCP_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, TCP_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    const bool use_tab = a.lntab != nullptr && a.metrics != nullptr;
+    if (use_tab) {
+        const int entries = min(3 * min(a.x.W, a.y.W) * 32 + 1, LN_TABLE_SIZE);
+        for (int k = threadIdx.x; k < entries; k += TCP_THREADS) tab[k] = __ldg(a.lntab + k);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    auto segment = [&](int kb, int& acc, int& kx, int& ky) {   // as in count_tc_kernel
+        const int unit = kb / blocks_per_L, within = (kb % blocks_per_L) * TC_TILE;
+        acc = unit == 0 ? 0 : unit == 1 ? 1 : unit < 4 ? 2 : 3;
+        const int first = acc == 2 ? 2 : acc == 3 ? 4 : unit;
+        const int into = (unit - first) * Lp + within;
+        kx = first * args.LpX + into;
+        ky = (acc == 3 ? 6 : first) * args.LpY + into;
+    };
+    auto tile_origin = [&](int tile, int& xt, int& yt) {       // bands of TC_BAND x tiles, column by column (operand reuse in L2)
+        const int band = tile / (TC_BAND * tiles_y), within = tile % (TC_BAND * tiles_y);
+        const int band_rows = min(TC_BAND, tiles_x - band * TC_BAND);
+        xt = (band * TC_BAND + within % band_rows) * TCP_TX;
+        yt = (within / band_rows) * TC_TILE;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long long kbg = 0;   // k-blocks issued so far, over all tiles: stage and phase of the smem ring
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int xt, yt;
+                tile_origin(tile, xt, yt);
+                for (int kb = 0; kb < kblocks; ++kb, ++kbg) {
+                    const int s = (int)(kbg % TCP_STAGES);
+                    int acc, kx, ky;
+                    segment(kb, acc, kx, ky);
+                    mbar_wait(empty + s, (uint32_t)((kbg / TCP_STAGES) & 1) ^ 1u);
+                    mbar_expect_tx(full + s, TCP_STAGE_X + TCP_STAGE_Y);
+                    tma_load_2d(sX + s * TCP_STAGE_X, &map_x, full + s, kx, a.x0 + xt);
+                    tma_load_2d(sY + s * TCP_STAGE_Y, &map_y, full + s, ky, a.y0 + yt);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TCP_TX >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+            long long kbg = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(acc_empty + as, (uint32_t)((it >> 1) & 1) ^ 1u);     // the epilogue has drained this accumulator set
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                int prev_acc = -1;
+                for (int kb = 0; kb < kblocks; ++kb, ++kbg) {
+                    const int s = (int)(kbg % TCP_STAGES);
+                    int acc, kx, ky;
+                    segment(kb, acc, kx, ky);
+                    mbar_wait(full + s, (uint32_t)((kbg / TCP_STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < TC_TILE / TC_UMMA_K; ++k)
+                        umma_i8(tmem + (uint32_t)(as * 4 * TCP_TX + acc * TCP_TX), umma_desc(sY + s * TCP_STAGE_Y, k * TC_UMMA_K),
+                                umma_desc(sX + s * TCP_STAGE_X, k * TC_UMMA_K), idesc, (acc == prev_acc || k > 0) ? 1u : 0u);
+                    prev_acc = acc;
+                    umma_commit(empty + s);
+                }
+                umma_commit(acc_full + as);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;                          // TMEM lanes [32 q, 32 q + 32): 32 y columns of the tile
+        const int cg = (warp - 4) >> 2;                  // 16 x rows of the tile
+        const long long* shared_tab = use_tab ? tab : nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            int xt, yt;
+            tile_origin(tile, xt, yt);
+            const int yc = yt + q * 32 + lane;
+            const bool col_ok = yc < a.ny;
+            const int ys = a.y0 + min(yc, a.ny - 1);
+            const int2 sy = __ldg(a.y.span + ys);
+            mbar_wait_relaxed(acc_full + as, (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 4 * TCP_TX);
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                const int r0 = cg * 16 + ch * 8;
+                int A0[8], A1[8], A2[8], A3[8];
+                tmem_ld8(lane_addr + (uint32_t)(0 * TCP_TX + r0), A0);
+                tmem_ld8(lane_addr + (uint32_t)(1 * TCP_TX + r0), A1);
+                tmem_ld8(lane_addr + (uint32_t)(2 * TCP_TX + r0), A2);
+                tmem_ld8(lane_addr + (uint32_t)(3 * TCP_TX + r0), A3);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ch == 1) {   // this warp holds everything it needs of the accumulator set: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty + as);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int xr = xt + r0 + k;
+                    if (xr < a.nx && col_ok) {
+                        const int n = A0[k];
+                        const int ts = (n + A1[k] - A2[k]) >> 2, tv = (n - A1[k]) >> 1;
+                        int gap = A3[k];
+                        const int xs = a.x0 + xr;
+                        if (n > 0 && gap > 0)
+                            gap -= gaps_outside_trim([&](int w) { return a.x.at(w, xs); }, [&](int w) { return a.y.at(w, ys); },
+                                                     __ldg(a.x.span + xs), sy);
+                        store_pair<true>(a, (long long)xr * a.ny + yc, n, tv, ts, n > 0 ? gap : 0, shared_tab);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 }  // namespace taxi

@@ -120,6 +120,7 @@ struct taxi_ctx {
     int no_coop = 0;                // option: never use the intra-task kernel for long pairs
     int metric_tables = 1;          // option: alignment-free kernels take JC / K2P from the fixed-point logarithm table where rows are short enough
     DevBuf<long long> lntab;        // ln k * 2^58, k = 0 .. 3 * LN_TABLE_COLS
+    int tc_persistent = 0;          // option: persistent form of the tensor-core counting kernel (count_tc_persistent_kernel)
     int tc_tile_x = 128;            // option: x rows per tile of the tensor-core counting kernel (128: one CTA per SM, 64: two)
     int count_kernel = 0;           // option: alignment-free rectangles on 0 = whichever fits, 1 = popcount kernel, 2 = tensor-core kernel
     int last_kernel = 0;            // 0 = none, 32 = gotoh_warp (int32), 16 = gotoh_pair16
@@ -1244,6 +1245,18 @@ static int enqueue_count(taxi_ctx* c, CountArgs a)
             const SeqSet& YY = yset(c);
             a.slab = 0;
             CountTcArgs t{a, std::min(XX.Lp, YY.Lp), XX.Lp, YY.Lp};
+            if (c->tc_persistent) {
+                // one CTA per SM walking a static tile list, contraction of the next tile under the epilogue of this one
+                const int ntiles = ((a.ny + TC_TILE - 1) / TC_TILE) * ((a.nx + TCP_TX - 1) / TCP_TX);
+                CUDA_TRY(cudaFuncSetAttribute(count_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCP_SMEM));
+                CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+                count_tc_persistent_kernel<<<std::min(ntiles, c->sms), TCP_THREADS, TCP_SMEM, c->stream>>>(XX.tc_map64, YY.tc_map, t);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+                c->launches += 1;
+                c->last_kernel = 9;
+                return TAXI_OK;
+            }
             const bool wide = c->tc_tile_x == 128;
             const int tx = wide ? 128 : 64;
             dim3 grid((unsigned)(((a.ny + TC_TILE - 1) / TC_TILE) * ((a.nx + tx - 1) / tx)));   // one-dimensional: count_tc_kernel orders the tiles itself
@@ -1425,6 +1438,7 @@ int taxi_set_option(taxi_ctx* c, const char* key, int value)
     if (std::strcmp(key, "sort_columns") == 0) { c->sort_columns = value; return TAXI_OK; }
     if (std::strcmp(key, "count_kernel") == 0) { c->count_kernel = value; return TAXI_OK; }
     if (std::strcmp(key, "metric_tables") == 0) { c->metric_tables = value; return TAXI_OK; }
+    if (std::strcmp(key, "tc_persistent") == 0) { c->tc_persistent = value; return TAXI_OK; }
     if (std::strcmp(key, "tc_tile_x") == 0) {
         if (value != 64 && value != 128) return fail(TAXI_E_ARG, "tc_tile_x must be 64 or 128");
         c->tc_tile_x = value;

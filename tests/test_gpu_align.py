@@ -615,9 +615,10 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
     cols = ys if ys is not None else xs
     nx, ny = len(xs), len(cols)
     results = {}
-    for kernel, tile_x in ((1, 64), (2, 64), (2, 128)):   # popcount; tensor cores with two CTAs per SM, with one
-        engine.set_option("count_kernel", kernel)
+    for kernel, tile_x in ((1, 64), (2, 64), (2, 128), (3, 64)):   # popcount; tensor cores: two CTAs per SM, one, persistent
+        engine.set_option("count_kernel", min(kernel, 2))
         engine.set_option("tc_tile_x", tile_x)
+        engine.set_option("tc_persistent", int(kernel == 3))
         try:
             full = engine.count_rect(0, nx, 0, ny)
             assert engine.last_kernel == (8 if kernel == 1 else 9)
@@ -625,12 +626,13 @@ def test_tensor_core_counts_equal_popcount_and_oracle(engine, case):
         finally:
             engine.set_option("count_kernel", 0)
             engine.set_option("tc_tile_x", 128)
+            engine.set_option("tc_persistent", 0)
         results[kernel, tile_x] = full
         assert np.array_equal(part["counts"], full["counts"][37:nx - 13, 11:ny - 18])
         assert np.array_equal(part["metrics"], full["metrics"][37:nx - 13, 11:ny - 18], equal_nan=True)
-    for tile_x in (64, 128):
-        assert np.array_equal(results[1, 64]["counts"], results[2, tile_x]["counts"]), tile_x
-        assert np.array_equal(results[1, 64]["metrics"], results[2, tile_x]["metrics"], equal_nan=True), tile_x
+    for key in ((2, 64), (2, 128), (3, 64)):
+        assert np.array_equal(results[1, 64]["counts"], results[key]["counts"]), key
+        assert np.array_equal(results[1, 64]["metrics"], results[key]["metrics"], equal_nan=True), key
     results[2] = results[2, 64]
     data, off = pack_strings(xs + (ys or []))
     px = rng.integers(0, nx, 3000).astype(np.int32)

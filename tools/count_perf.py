@@ -24,6 +24,7 @@ import os  # noqa: E402
 eng = Engine(0)
 eng.set_option("count_kernel", int(os.environ.get("TAXI_COUNT_KERNEL", "0")))   # 1 = popcount, 2 = tensor cores
 eng.set_option("tc_tile_x", int(os.environ.get("TAXI_TC_TILE_X", "128")))        # x rows per tile: 64 (two CTAs per SM) or 128
+eng.set_option("tc_persistent", int(os.environ.get("TAXI_TC_PERSISTENT", "0")))   # 1: persistent form of the tensor-core kernel
 eng.set_option("metric_tables", int(os.environ.get("TAXI_METRIC_TABLES", "1")))   # 0: floating-point JC / K2P in the count kernels
 eng.load(seqs, 0)
 counts = torch.empty((n * n, 4), dtype=torch.int32, device="cuda")
@@ -46,5 +47,5 @@ for it in range(3):      # counts only: what the fp64 metric epilogue costs
     best_counts = ms if best_counts is None else min(best_counts, ms)
 pairs = n * n
 bytes_alg = n * W * 16 + pairs * 48          # planes read once + 16 B counts + 32 B metrics per pair
-print(json.dumps(dict(metric_tables=int(os.environ.get("TAXI_METRIC_TABLES", "1")), tc_tile_x=int(os.environ.get("TAXI_TC_TILE_X", "128")), kernel={8: "count_rect_kernel (popcount)", 9: "count_tc_kernel (tcgen05 int8)"}.get(eng.last_kernel), workload=f"{n} x {n} pre-aligned pairs, {width} columns", pairs=pairs, kernel_ms=round(best, 3), counts_only_ms=round(best_counts, 3),
+print(json.dumps(dict(persistent=int(os.environ.get("TAXI_TC_PERSISTENT", "0")), metric_tables=int(os.environ.get("TAXI_METRIC_TABLES", "1")), tc_tile_x=int(os.environ.get("TAXI_TC_TILE_X", "128")), kernel={8: "count_rect_kernel (popcount)", 9: "count_tc_kernel (tcgen05 int8)"}.get(eng.last_kernel), workload=f"{n} x {n} pre-aligned pairs, {width} columns", pairs=pairs, kernel_ms=round(best, 3), counts_only_ms=round(best_counts, 3),
                       pairs_per_s=pairs / best * 1e3, hbm_gbs=bytes_alg / best / 1e6, checksum=int(counts.sum().item()))))
