@@ -153,6 +153,14 @@ int taxi_count_pairs(taxi_ctx* ctx, const int32_t* px, const int32_t* py, int64_
  * of metric column `metric` (0..3) over each row of an nx x ny metrics matrix (device pointer,
  * 4 doubles per pair); NaN never wins.  out_index[x] = -1 when the whole row is undefined.
  */
+/*
+ * The metric formulas on their own (distances.py:319-348 applied to counts instead of strings): n tuples
+ * {same, transitions, transversions, internal gap columns} -> {p, p-gaps, jc, k2p} per tuple, NaN where the
+ * reference yields None.  form 0: the floating-point form every aligner epilogue uses (operation for
+ * operation the reference's formulas); form 1: the table form of the alignment-free kernels (ln k in fixed
+ * point; tuples of more than 2048 compared columns fall back to form 0).  Host pointers.
+ */
+int taxi_metrics_from_counts(taxi_ctx* ctx, const int32_t* counts, int64_t n, int32_t form, double* out_metrics);
 int taxi_argmin_rows_device(taxi_ctx* ctx, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
                             int32_t* out_index_host, double* out_value_host);
 

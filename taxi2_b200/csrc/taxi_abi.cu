@@ -1361,6 +1361,39 @@ int taxi_count_pairs(taxi_ctx* c, const int32_t* px, const int32_t* py, int64_t 
     return finish_align(c);
 }
 
+// the four metrics of n count tuples {same, transitions, transversions, gap columns}: the epilogue every kernel
+// ends with, on its own (one thread per tuple)
+__global__ void metrics_from_counts_kernel(const int32_t* __restrict__ counts, long long n, const long long* __restrict__ lntab,
+                                           double* __restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int4 c = *reinterpret_cast<const int4*>(counts + 4 * k);
+    double m[4];
+    // the table covers the logarithm arguments of tuples with at most LN_TABLE_COLS compared columns
+    if (lntab && c.x >= 0 && c.y >= 0 && c.z >= 0 && (long long)c.x + c.y + c.z <= LN_TABLE_COLS)
+        metrics_from_counts_table(c.x, c.y, c.z, c.w, m, [&](int i) { return __ldg(lntab + i); });
+    else metrics_from_counts(c.x, c.y, c.z, c.w, m);
+    reinterpret_cast<double2*>(out + 4 * k)[0] = make_double2(m[0], m[1]);
+    reinterpret_cast<double2*>(out + 4 * k)[1] = make_double2(m[2], m[3]);
+}
+
+int taxi_metrics_from_counts(taxi_ctx* c, const int32_t* counts, int64_t n, int32_t form, double* out_metrics)
+{
+    int rc = check_ctx(c, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!counts || !out_metrics)) || (form != 0 && form != 1)) return fail(TAXI_E_ARG, "bad count tuples / form");
+    if (n == 0) return TAXI_OK;
+    ON_DEVICE(c->device);
+    if ((rc = reserve_outputs(c, n, TAXI_OUT_COUNTS | TAXI_OUT_METRICS))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->d_counts.p, counts, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    metrics_from_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_counts.p, (long long)n, form ? c->lntab.p : nullptr, c->d_metrics.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_metrics, c->d_metrics.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return TAXI_OK;
+}
+
 int taxi_argmin_rows_device(taxi_ctx* c, const double* d_metrics, int32_t nx, int32_t ny, int32_t metric,
                             int32_t* out_index_host, double* out_value_host)
 {

@@ -273,6 +273,15 @@ class Engine:
         flags = (N.OUT_COUNTS if d_counts else 0) | (N.OUT_METRICS if d_metrics else 0)
         N.check(self._lib.taxi_count_rect_device(self._ctx, x0, nx, y0, ny, flags, C.c_void_p(d_counts), C.c_void_p(d_metrics)))
 
+    def metrics_from_counts(self, counts, table: bool = False) -> np.ndarray:
+        """(n, 4) count tuples {same, ts, tv, gaps} -> (n, 4) {p, p-gaps, jc, k2p}, NaN = undefined: the
+        epilogue of every kernel on its own (table=True: the fixed-point logarithm table of the
+        alignment-free kernels)."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1, 4)
+        out = np.empty((len(counts), 4), dtype=np.float64)
+        N.check(self._lib.taxi_metrics_from_counts(self._ctx, _p(counts), len(counts), int(bool(table)), _p(out)))
+        return out
+
     def argmin_rows_device(self, d_metrics: int, nx: int, ny: int, metric: int) -> tuple[np.ndarray, np.ndarray]:
         idx = np.zeros(nx, dtype=np.int32)
         val = np.zeros(nx, dtype=np.float64)

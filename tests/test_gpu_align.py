@@ -689,6 +689,28 @@ def test_table_form_of_the_metric_epilogue(engine):
     assert ((nn > 0) & (nn - 2 * ts - tv == 0)).any() and ((nn > 0) & (nn - 2 * tv == 0)).any() and ((nn > 0) & (3 * nn - 4 * (ts + tv) == 0)).any()
 
 
+def test_metric_formulas_on_every_small_count_tuple(engine):
+    """taxi_metrics_from_counts: the epilogue of every kernel on its own.  Every (same, ts, tv) with
+    n <= 72 (and a few gap counts), plus random tuples up to 2048 and beyond, through the
+    floating-point form and the table form, against the oracle's libm formulas: same None pattern,
+    p / p-gaps bit for bit, JC / K2P within 1e-12; zero counts and saturated tuples included."""
+    rng = np.random.default_rng(77)
+    small = np.array([(n - ts - tv, ts, tv, g) for n in range(0, 73) for ts in range(n + 1) for tv in range(n + 1 - ts)
+                      for g in (0, 3)], dtype=np.int32)
+    n = rng.integers(1, 2049, 40000)
+    ts = (rng.random(40000) * (n + 1)).astype(np.int64)
+    tv = (rng.random(40000) * (n - ts + 1)).astype(np.int64)
+    big = np.stack([n - ts - tv, ts, tv, rng.integers(0, 50, 40000)], axis=1).astype(np.int32)
+    long_rows = big.copy()
+    long_rows[:, 0] += 5000                                   # beyond the table: both forms take the floating-point route
+    counts = np.concatenate([small, big, long_rows])
+    want = np.array([oracle.metrics(c) for c in counts])
+    for table in (False, True):
+        got = engine.metrics_from_counts(counts, table=table)
+        assert_metrics_close(got, want)
+    assert np.isnan(want[:, 2]).sum() > 1000 and np.isnan(want[:, 3]).sum() > 1000 and (want[:, 3] > 5).any()
+
+
 def test_intra_task_kernel_for_few_long_pairs(engine):
     """A handful of pairs spanning many stripes: the stripes of each pair are pipelined over the
     warps of a CTA (gotoh_coop_kernel) instead of one warp running them all.  Same scores, counts
