@@ -279,9 +279,14 @@ int taxi_format_aligned_pairs(const char* path, int32_t first_record,
                 out += '\n';
                 const size_t at = out.size();
                 out.resize(at + len);
+                // '-' where either side is a gap, '|' where the symbols agree, '.' otherwise: written without
+                // branches over raw pointers so that the compiler turns it into byte-wise SIMD compares / selects
+                char* __restrict__ pat = &out[at];
                 for (size_t k = 0; k < len; ++k) {
                     const uint8_t a = ax[k], c = ay[k];
-                    out[at + k] = (a == '-' || c == '-') ? '-' : (a == c ? '|' : '.');
+                    const uint8_t gap = (uint8_t)-(uint8_t)((a == '-') | (c == '-')), eq = (uint8_t)-(uint8_t)(a == c);
+                    const uint8_t base = (uint8_t)(('|' & eq) | ('.' & (uint8_t)~eq));
+                    pat[k] = (char)(('-' & gap) | (base & (uint8_t)~gap));
                 }
                 out += '\n';
                 out.append(reinterpret_cast<const char*>(ay), len);
