@@ -67,14 +67,14 @@ inline bool append_fixed(std::string& out, double v, int decimals)
         if (rem > half || (rem == half && (q & 1))) q += 1;
     }
     if (q >> 64) return false;
-    const uint64_t digits = (uint64_t)q, whole = digits / kPow10[decimals], frac = digits % kPow10[decimals];
+    // q = the value in units of the last decimal: its low `decimals` digits are the fraction, the rest the
+    // whole part (at least one digit) -- peeled off from the right, no division by a run-time power of ten
+    uint64_t digits = (uint64_t)q;
     char buf[48];
     int at = (int)sizeof buf;
-    uint64_t f = frac;
-    for (int k = 0; k < decimals; ++k) { buf[--at] = (char)('0' + f % 10); f /= 10; }
+    for (int k = 0; k < decimals; ++k) { buf[--at] = (char)('0' + digits % 10); digits /= 10; }
     if (decimals) buf[--at] = '.';
-    uint64_t w = whole;
-    do { buf[--at] = (char)('0' + w % 10); w /= 10; } while (w);
+    do { buf[--at] = (char)('0' + digits % 10); digits /= 10; } while (digits);
     if (negative) buf[--at] = '-';
     out.append(buf + at, sizeof buf - (size_t)at);
     return true;
